@@ -1,0 +1,171 @@
+"""Thin object wrapper over the C ABI (include/rl_b200.h).  One Context = one rl_ctx = one GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from .desc import SceneDesc
+
+
+class Context:
+    def __init__(self, device_id: int = 0):
+        self.lib = A.load_library()
+        h = C.c_void_p()
+        rc = self.lib.rl_create(int(device_id), C.byref(h))
+        if rc != A.RL_OK:
+            msg = self.lib.rl_last_error(None)
+            raise A.RlError(rc, (msg or b"").decode())
+        self.h = h
+        self.device_id = device_id
+        self._scene = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != A.RL_OK:
+            raise A.RlError(rc, (self.lib.rl_last_error(self.h) or b"").decode())
+
+    # ---- device / scene ----------------------------------------------------------------------
+    def device_info(self) -> dict:
+        sm, ma, mi, hb = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self._check(self.lib.rl_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi),
+                                            C.byref(hb)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hb.value}
+
+    def scene_upload(self, desc: SceneDesc):
+        d = desc.freeze()
+        self._check(self.lib.rl_scene_upload(self.h, C.byref(d)))
+        self._scene = desc
+
+    def scene_info(self) -> A.rl_scene_info:
+        info = A.rl_scene_info()
+        self._check(self.lib.rl_scene_info_get(self.h, C.byref(info)))
+        return info
+
+    def set_instrumented(self, enabled: bool):
+        self._check(self.lib.rl_set_instrumented(self.h, int(bool(enabled))))
+
+    def lbvh_download(self) -> dict:
+        info = self.scene_info()
+        n, m = info.n_bvh_prims, info.n_bvh_nodes
+        out = {
+            "prim_aabb": np.zeros((max(n, 1), 6), np.float32),
+            "prim_node": np.zeros(max(n, 1), np.int32),
+            "morton": np.zeros(max(n, 1), np.uint64),
+            "sorted_prim": np.zeros(max(n, 1), np.int32),
+            "left": np.zeros(max(m, 1), np.int32),
+            "right": np.zeros(max(m, 1), np.int32),
+            "parent": np.zeros(max(n + m, 1), np.int32),
+            "node_aabb": np.zeros((max(m, 1), 6), np.float32),
+        }
+        h = A.rl_lbvh_host()
+        h.prim_aabb = out["prim_aabb"].ctypes.data_as(C.POINTER(C.c_float))
+        h.prim_node = out["prim_node"].ctypes.data_as(C.POINTER(C.c_int32))
+        h.morton = out["morton"].ctypes.data_as(C.POINTER(C.c_uint64))
+        h.sorted_prim = out["sorted_prim"].ctypes.data_as(C.POINTER(C.c_int32))
+        h.left = out["left"].ctypes.data_as(C.POINTER(C.c_int32))
+        h.right = out["right"].ctypes.data_as(C.POINTER(C.c_int32))
+        h.parent = out["parent"].ctypes.data_as(C.POINTER(C.c_int32))
+        h.node_aabb = out["node_aabb"].ctypes.data_as(C.POINTER(C.c_float))
+        self._check(self.lib.rl_lbvh_download(self.h, C.byref(h)))
+        out = {k: (v[:n] if k in ("prim_aabb", "prim_node", "morton", "sorted_prim") else
+                   v[:m] if k in ("left", "right", "node_aabb") else v[:n + m])
+               for k, v in out.items()}
+        out["scene_lo"] = np.array(list(h.scene_lo), np.float32)
+        out["scene_hi"] = np.array(list(h.scene_hi), np.float32)
+        out["n_prims"], out["n_nodes"] = n, m
+        return out
+
+    # ---- ray batches -------------------------------------------------------------------------
+    def trace_batch(self, origins, directions, times=None):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        rays = np.zeros((n, 8), np.float32)
+        rays[:, 0:3] = o
+        rays[:, 3:6] = d
+        if times is not None:
+            rays[:, 6] = np.asarray(times, np.float32)
+        hits = np.zeros(n, dtype=np.dtype([("node", np.int32), ("t", np.float32),
+                                           ("u", np.float32), ("v", np.float32)]))
+        self._check(self.lib.rl_trace_batch(self.h, rays.ctypes.data_as(C.POINTER(A.rl_ray)),
+                                            C.c_uint64(n),
+                                            hits.ctypes.data_as(C.POINTER(A.rl_hit))))
+        return hits
+
+    # ---- renders (host buffers) ----------------------------------------------------------------
+    def render_rtc(self, cam: A.rl_rtc_camera, aa_samples: int = 1, out: np.ndarray | None = None):
+        if out is None:
+            out = np.empty((cam.vsize, cam.hsize, 3), np.float32)
+        stats = A.rl_stats()
+        self._check(self.lib.rl_render_rtc(self.h, C.byref(cam), C.c_uint32(aa_samples),
+                                           out.ctypes.data_as(C.POINTER(C.c_float)),
+                                           C.byref(stats)))
+        return out, stats
+
+    def ow_image_height(self, cam: A.rl_ow_camera) -> int:
+        return int(self.lib.rl_ow_image_height(C.byref(cam)))
+
+    def ow_num_chunks(self, cam: A.rl_ow_camera) -> int:
+        return int(self.lib.rl_ow_num_chunks(C.byref(cam)))
+
+    def render_ow(self, cam: A.rl_ow_camera, first_sample: int = 0, out: np.ndarray | None = None):
+        h = self.ow_image_height(cam)
+        if out is None:
+            out = np.empty((h, cam.image_width, 3), np.float32)
+        stats = A.rl_stats()
+        self._check(self.lib.rl_render_ow(self.h, C.byref(cam), C.c_uint32(first_sample),
+                                          out.ctypes.data_as(C.POINTER(C.c_float)),
+                                          C.byref(stats)))
+        return out, stats
+
+    # ---- renders (device buffers; multi-GPU plumbing) -----------------------------------------------
+    @staticmethod
+    def _jobs(jobs):
+        arr = (A.rl_job * len(jobs))()
+        for i, j in enumerate(jobs):
+            arr[i] = A.rl_job(*j)
+        return arr
+
+    def render_rtc_device(self, cam, aa_samples, jobs, d_out_ptr: int, stream: int = 0):
+        stats = A.rl_stats()
+        arr = self._jobs(jobs)
+        self._check(self.lib.rl_render_rtc_device(self.h, C.byref(cam), C.c_uint32(aa_samples), arr,
+                                                  len(jobs), C.c_void_p(d_out_ptr),
+                                                  C.c_void_p(stream), C.byref(stats)))
+        return stats
+
+    def render_ow_device(self, cam, first_sample, jobs, d_partial_ptr: int, stream: int = 0):
+        stats = A.rl_stats()
+        arr = self._jobs(jobs)
+        self._check(self.lib.rl_render_ow_device(self.h, C.byref(cam), C.c_uint32(first_sample), arr,
+                                                 len(jobs), C.c_void_p(d_partial_ptr),
+                                                 C.c_void_p(stream), C.byref(stats)))
+        return stats
+
+    def ow_reduce_device(self, cam, d_partial_ptr: int, d_out_ptr: int, stream: int = 0):
+        self._check(self.lib.rl_ow_reduce_device(self.h, C.byref(cam), C.c_void_p(d_partial_ptr),
+                                                 C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    """The context `Camera.render` uses (cuda:LOCAL_RANK or cuda:0)."""
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx

@@ -1,0 +1,207 @@
+"""Scene builders written against the mirrored reference API.
+
+* the reference's own golden-test scenes (RTC/tests/ray_tracer.rs:56-368,
+  OW/tests/ray_tracing_one_weekend.rs:14-75), and
+* the five BASELINE.json configs: C1 three spheres on a plane, C2 mirror scene,
+  C3 teapot, C4 RTIOW cover scene (OW/examples/bouncing_spheres.rs:16-134), C5 Cornell box + spot
+  (OW/examples/cow.rs:17-139).
+
+Mesh / texture inputs come from rendering_learning_b200/assets/*.npz (parsed from the reference's
+objs/ by tests/golden/make_fixtures.py, because /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+from . import rtc
+
+ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+# std::f64::consts — decimal literals as in Rust's core (FRAC_PI_3 / FRAC_PI_6 are NOT equal to
+# math.pi/3, math.pi/6: the literals round to the nearest double of the true quotient)
+FRAC_PI_2 = 1.57079632679489661923132169163975144
+FRAC_PI_3 = 1.04719755119659774615421446109316763
+FRAC_PI_4 = 0.785398163397448309615660845819875721
+FRAC_PI_6 = 0.52359877559829887307710723054658381
+
+
+def _inv(m):
+    return rtc.InvertibleMatrix.try_from(m)
+
+
+# --------------------------------------------------------------------------------------------------
+# RTC
+# --------------------------------------------------------------------------------------------------
+
+def rtc_mirror_world() -> rtc.World:
+    """RTC/tests/ray_tracer.rs:56-225 (`test_mirror_scene`, world part)."""
+    T = rtc.transformation
+    gs1 = rtc.Transformed.new(rtc.Sphere.unit(), _inv(T.translation(-0.5, 0.0, 0.0)))
+    gs2 = rtc.Transformed.new(rtc.Sphere.unit(), _inv(T.translation(0.5, 0.0, 0.0)))
+    sphere_group = rtc.Bounded.new(rtc.Transformed.new(
+        rtc.Group.new([gs1, gs2]),
+        _inv(T.sequence([T.rotation_z(FRAC_PI_2), T.translation(-2.0, 2.0, 0.0)]))))
+    floor = rtc.Plane(rtc.Material(
+        surface=rtc.Surface.Pattern(rtc.Checker3d(a=rtc.color.white(), b=rtc.color.black(),
+                                                  transform=_inv(T.translation(0.0, -0.01, 0.0)))),
+        specular=0.0, reflectivity=0.02))
+    left_wall = rtc.Transformed.new(
+        rtc.Plane(rtc.Material(surface=rtc.color.white(), specular=1.0, reflectivity=0.9,
+                               shininess=400.0, diffuse=0.0)),
+        _inv(T.sequence([T.rotation_x(FRAC_PI_2), T.rotation_y(-FRAC_PI_3),
+                         T.translation(-8.0, 0.0, 0.0)])))
+    right_wall = rtc.Transformed.new(
+        rtc.Plane(rtc.Material(surface=rtc.color.white(), specular=1.0, reflectivity=1.0,
+                               shininess=400.0, diffuse=0.0)),
+        _inv(T.sequence([T.rotation_x(FRAC_PI_2), T.rotation_y(FRAC_PI_4),
+                         T.translation(10.0, 0.0, 0.0)])))
+    middle_wall = rtc.Transformed.new(
+        rtc.Plane(rtc.Material(surface=rtc.Color(0.945, 0.788, 0.647), specular=0.1,
+                               shininess=50.0)),
+        _inv(T.sequence([T.rotation_x(FRAC_PI_2), T.translation(0.0, 0.0, 7.0)])))
+    ball = rtc.Transformed.new(
+        rtc.Sphere(rtc.Material(surface=rtc.Color(0.059, 0.322, 0.729), diffuse=0.3, specular=1.0,
+                                reflectivity=0.9, transparency=0.75, refractive_index=1.52)),
+        _inv(T.translation(0.0, 2.0, 0.0)))
+    inner_air_pocket = rtc.Transformed.new(
+        rtc.Sphere(rtc.Material(surface=rtc.color.white(), ambient=0.0, diffuse=0.0, specular=0.0,
+                                transparency=1.0, refractive_index=1.0, reflectivity=1.0)),
+        _inv(T.sequence([T.scaling(0.5, 0.5, 0.5), T.translation(0.0, 2.0, 0.0)])))
+    behind_cube = rtc.Transformed.new(
+        rtc.Cube(rtc.Material(surface=rtc.Surface.Pattern(rtc.Stripe(
+            a=rtc.Color(0.545, 0.0, 0.0), b=rtc.Color(0.0, 0.392, 0.0),
+            transform=_inv(T.scaling(0.2, 1.0, 1.0)))))),
+        _inv(T.translation(3.0, 0.0, -10.0)))
+    behind_wall = rtc.Transformed.new(
+        rtc.Plane(rtc.Material(surface=rtc.Color(0.678, 0.847, 0.902), specular=0.1,
+                               shininess=50.0)),
+        _inv(T.sequence([T.rotation_x(FRAC_PI_2), T.translation(0.0, 0.0, -100.0)])))
+    light = rtc.PointLight(position=rtc.Point3d(-10.0, 10.0, -10.0), intensity=rtc.color.white())
+    return rtc.World(objects=[floor, left_wall, right_wall, middle_wall, ball, inner_air_pocket,
+                              behind_cube, behind_wall, sphere_group], lights=[light])
+
+
+def rtc_mirror_scene(hsize=300, vsize=200) -> rtc.Scene:
+    """RTC/tests/ray_tracer.rs:227-240 camera; BASELINE config C2 at 3840x2160."""
+    T = rtc.transformation
+    cam = rtc.Camera.new(hsize, vsize, FRAC_PI_3, _inv(T.view_transform(
+        rtc.Point3d(0.0, 2.0, -7.0), rtc.Point3d(0.0, 1.5, 0.0), rtc.Vec3d(0.0, 1.0, 0.0))))
+    return rtc.Scene(camera=cam, world=rtc_mirror_world())
+
+
+def load_mesh(name: str) -> dict:
+    return dict(np.load(os.path.join(ASSETS, name + ".npz")))
+
+
+def rtc_teapot_object() -> rtc.Object:
+    """`WavefrontObj::parse(teapot-low.obj).to_object()` rebuilt from the parsed fixture."""
+    m = load_mesh("teapot_low")
+    mat = rtc.Material()
+    tris = []
+    P, N = m["tri_p"], m["tri_n"]
+    for i in range(P.shape[0]):
+        pts = [tuple(P[i, k]) for k in range(3)]
+        if m["tri_smooth"][i]:
+            tris.append(rtc.Triangle.smooth([(pts[k], tuple(N[i, k])) for k in range(3)], mat))
+        else:
+            tris.append(rtc.Triangle.flat(pts, mat))
+    return rtc.Bounded.new(rtc.Group.new(tris))
+
+
+def rtc_obj_scene(hsize=300, vsize=200, obj: rtc.Object | None = None) -> rtc.Scene:
+    """RTC/tests/ray_tracer.rs:242-275 (`test_obj_scene`); BASELINE config C3 at 3840x2160."""
+    T = rtc.transformation
+    o = rtc.Transformed.new(obj if obj is not None else rtc_teapot_object(),
+                            _inv(T.sequence([T.rotation_x(-FRAC_PI_2)])))
+    light = rtc.PointLight(position=rtc.Point3d(-2.0, 20.0, -30.0), intensity=rtc.color.white())
+    world = rtc.World(objects=[o], lights=[light])
+    cam = rtc.Camera.new(hsize, vsize, FRAC_PI_3, _inv(T.view_transform(
+        rtc.Point3d(0.0, 15.0, -30.0), rtc.Point3d(0.0, 5.0, 0.0), rtc.Vec3d(0.0, 1.0, 0.0))))
+    return rtc.Scene(camera=cam, world=world)
+
+
+def rtc_csg_scene(hsize=300, vsize=200) -> rtc.Scene:
+    """RTC/tests/ray_tracer.rs:277-368 (`test_csg_scene`)."""
+    T = rtc.transformation
+    room = rtc.Transformed.new(
+        rtc.Cube(rtc.Material(
+            surface=rtc.Surface.Pattern(rtc.Checker3d(
+                a=rtc.Color(0.6, 0.6, 0.6), b=rtc.Color(0.7, 0.7, 0.7),
+                transform=_inv(T.sequence([T.translation(0.01, 0.01, 0.01),
+                                           T.scaling(0.02, 0.02, 0.02)])))),
+            reflectivity=0.0, ambient=0.5, shininess=10.0, diffuse=0.3, specular=0.3)),
+        _inv(T.scaling(50.0, 50.0, 50.0)))
+    hollow_circle = rtc.Csg(
+        left=rtc.Sphere(rtc.Material(surface=rtc.color.green())),
+        right=rtc.Transformed.new(rtc.Sphere(rtc.Material(surface=rtc.color.blue())),
+                                  _inv(T.scaling(0.7, 0.7, 0.7))),
+        operation=rtc.CsgOperation.Difference)
+    obj = rtc.Csg(
+        left=hollow_circle,
+        right=rtc.Transformed.new(rtc.Cube(rtc.Material(surface=rtc.color.red())),
+                                  _inv(T.translation(1.0, 0.0, 0.0))),
+        operation=rtc.CsgOperation.Difference)
+    obj_t = rtc.Transformed.new(obj, _inv(T.sequence([T.rotation_y(FRAC_PI_6),
+                                                      T.scaling(7.0, 7.0, 7.0)])))
+    l1 = rtc.PointLight(position=rtc.Point3d(-2.0, 20.0, -30.0), intensity=rtc.Color(0.5, 0.5, 0.5))
+    l2 = rtc.PointLight(position=rtc.Point3d(10.0, 20.0, -30.0), intensity=rtc.Color(0.5, 0.5, 0.5))
+    world = rtc.World(objects=[room, obj_t], lights=[l1, l2])
+    cam = rtc.Camera.new(hsize, vsize, FRAC_PI_3, _inv(T.view_transform(
+        rtc.Point3d(0.0, 0.0, -30.0), rtc.Point3d(0.0, 0.0, 0.0), rtc.Vec3d(0.0, 1.0, 0.0))))
+    return rtc.Scene(camera=cam, world=world)
+
+
+def rtc_three_spheres_scene(hsize=1920, vsize=1080) -> rtc.Scene:
+    """BASELINE config C1: book ch. 9 poses assembled from the reference API."""
+    T = rtc.transformation
+    floor = rtc.Plane(rtc.Material(surface=rtc.Color(1.0, 0.9, 0.9), specular=0.0))
+    middle = rtc.Transformed.new(
+        rtc.Sphere(rtc.Material(surface=rtc.Color(0.1, 1.0, 0.5), diffuse=0.7, specular=0.3)),
+        _inv(T.translation(-0.5, 1.0, 0.5)))
+    right = rtc.Transformed.new(
+        rtc.Sphere(rtc.Material(surface=rtc.Color(0.5, 1.0, 0.1), diffuse=0.7, specular=0.3)),
+        _inv(matmul_seq(T.translation(1.5, 0.5, -0.5), T.scaling(0.5, 0.5, 0.5))))
+    left = rtc.Transformed.new(
+        rtc.Sphere(rtc.Material(surface=rtc.Color(1.0, 0.8, 0.1), diffuse=0.7, specular=0.3)),
+        _inv(matmul_seq(T.translation(-1.5, 0.33, -0.75), T.scaling(0.33, 0.33, 0.33))))
+    light = rtc.PointLight(position=rtc.Point3d(-10.0, 10.0, -10.0), intensity=rtc.color.white())
+    world = rtc.World(objects=[floor, middle, right, left], lights=[light])
+    cam = rtc.Camera.new(hsize, vsize, FRAC_PI_3, _inv(T.view_transform(
+        rtc.Point3d(0.0, 1.5, -5.0), rtc.Point3d(0.0, 1.0, 0.0), rtc.Vec3d(0.0, 1.0, 0.0))))
+    return rtc.Scene(camera=cam, world=world)
+
+
+def matmul_seq(*ms):
+    """a * b * c ... (left to right matrix product, `&a * &b` in the reference)."""
+    acc = ms[0]
+    for m in ms[1:]:
+        acc = rtc.matmul(acc, m)
+    return acc
+
+
+# --------------------------------------------------------------------------------------------------
+# OW
+# --------------------------------------------------------------------------------------------------
+
+def ow_test_scene():
+    """OW/tests/ray_tracing_one_weekend.rs:14-75 (`test_scene`): returns (world, CameraParams)."""
+    from . import ow
+    world = [
+        ow.Sphere(ow.Center.Stationary(ow.Point3(0.0, -100.5, -1.0)), 100.0,
+                  ow.Lambertian(ow.SolidColor(ow.Color(0.8, 0.8, 0.0)))),
+        ow.Sphere(ow.Center.Stationary(ow.Point3(0.0, 0.0, -1.2)), 0.5,
+                  ow.Lambertian(ow.SolidColor(ow.Color(0.1, 0.2, 0.5)))),
+        ow.Sphere(ow.Center.Stationary(ow.Point3(-1.0, 0.0, -1.0)), 0.5, ow.Dielectric(1.5)),
+        ow.Sphere(ow.Center.Stationary(ow.Point3(-1.0, 0.0, -1.0)), 0.4, ow.Dielectric(1.0 / 1.5)),
+        ow.Sphere(ow.Center.Stationary(ow.Point3(1.0, 0.0, -1.0)), 0.5,
+                  ow.Metal(ow.Color(0.8, 0.6, 0.2), 1.0)),
+    ]
+    params = ow.CameraParams(aspect_ratio=16.0 / 9.0, image_width=300, samples_per_pixel=10,
+                             max_depth=10, vfov=20.0, lookfrom=ow.Point3(-2.0, 2.0, 1.0),
+                             lookat=ow.Point3(0.0, 0.0, -1.0), vup=ow.Vec3(0.0, 1.0, 0.0),
+                             defocus_angle=10.0, focus_dist=3.4,
+                             background=ow.Color(0.7, 0.8, 1.0), seed=0)
+    return world, params
