@@ -182,3 +182,23 @@ def chacha8_u64(seed: int, stream: int, n: int) -> np.ndarray:
     lib().orc_chacha8_u64(C.c_uint64(seed), C.c_uint64(stream), C.c_int(n),
                           out.ctypes.data_as(C.POINTER(C.c_uint64)))
     return out
+
+
+# ---- LBVH host rebuild ---------------------------------------------------------------------------
+
+def lbvh_build(prim_aabb: np.ndarray) -> dict:
+    a = np.ascontiguousarray(prim_aabb, np.float32).reshape(-1, 6)
+    n = a.shape[0]
+    m = max(n - 1, 0)
+    out = {"morton": np.zeros(max(n, 1), np.uint64), "sorted_prim": np.zeros(max(n, 1), np.int32),
+           "left": np.zeros(max(m, 1), np.int32), "right": np.zeros(max(m, 1), np.int32),
+           "parent": np.zeros(max(n + m, 1), np.int32), "node_aabb": np.zeros((max(m, 1), 6), np.float32),
+           "bounds": np.zeros(6, np.float32)}
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    lib().orc_lbvh_build(fp(a), C.c_int(n), out["morton"].ctypes.data_as(C.POINTER(C.c_uint64)),
+                         _ip(out["sorted_prim"]), _ip(out["left"]), _ip(out["right"]), _ip(out["parent"]),
+                         fp(out["node_aabb"]), fp(out["bounds"]))
+    out["morton"], out["sorted_prim"] = out["morton"][:n], out["sorted_prim"][:n]
+    out["left"], out["right"], out["node_aabb"] = out["left"][:m], out["right"][:m], out["node_aabb"][:m]
+    out["parent"] = out["parent"][:n + m]
+    return out

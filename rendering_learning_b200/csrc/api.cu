@@ -1,0 +1,525 @@
+// C ABI of librl_b200.so (include/rl_b200.h): context, scene upload (flatten -> HBM -> LBVH build),
+// ray batches, renders.  No CPU fallback anywhere: without an sm_100 device rl_create fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device.cuh"
+#include "kernels.h"
+#include "lbvh.h"
+#include "scene.h"
+
+namespace rl {
+bool invert_affine_4x4(const double* m16, double* inv12, std::string* err);
+}
+
+using namespace rl;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes ? bytes : 16;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
+
+struct rl_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string error;
+    bool instrumented = false;
+    bool has_scene = false;
+    // scene buffers
+    DevBuf prims, tri_verts, tri_shade, xforms, spheres, quads, sphere_node, quad_node, materials, textures,
+        images, lights, nodes;
+    std::vector<DevBuf> image_texels;
+    DevBuf bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
+        node_aabb, lbvh_counters;
+    DevScene ds{};
+    rl_scene_info info{};
+    float upload_ms = 0.0f;
+    int upload_launches = 0;
+    // work buffers
+    DevBuf counters, queue, jobs, prefix, frame, partial, rays, hits;
+};
+
+#define CK(ctx, call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            (ctx)->error = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return RL_E_CUDA;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+static int fail(rl_ctx* c, int code, const std::string& msg) {
+    c->error = msg;
+    return code;
+}
+
+template <class T>
+static cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = b.reserve(v.size() * sizeof(T));
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+extern "C" {
+
+int rl_abi_version(void) { return RL_B200_ABI_VERSION; }
+
+const char* rl_last_error(const rl_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rl_create(int device_id, rl_ctx** out) {
+    if (!out) {
+        g_create_error = "rl_create: out is NULL";
+        return RL_E_INVALID;
+    }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("no CUDA device visible (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                         "); this library has no CPU fallback";
+        return RL_E_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= n) {
+        g_create_error = "device id out of range";
+        return RL_E_INVALID;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device_id);
+    if (e != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        return RL_E_CUDA;
+    }
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "device %d is sm_%d%d; librl_b200 carries sm_100a code only (no fallback)", device_id,
+                 prop.major, prop.minor);
+        g_create_error = buf;
+        return RL_E_NO_DEVICE;
+    }
+    rl_ctx* c = new rl_ctx();
+    c->device = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->hbm_bytes = prop.totalGlobalMem;
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = c->counters.reserve(sizeof(Counters))) != cudaSuccess || (e = c->queue.reserve(sizeof(unsigned long long))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return RL_E_CUDA;
+    }
+    *out = c;
+    return RL_OK;
+}
+
+void rl_destroy(rl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
+                     &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->bvh_aabb,
+                     &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
+                     &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
+                     &c->jobs, &c->prefix, &c->frame, &c->partial, &c->rays, &c->hits};
+    for (DevBuf* b : all) b->release();
+    for (DevBuf& b : c->image_texels) b.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rl_device_info(rl_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes) {
+    if (!c) return RL_E_INVALID;
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)c->hbm_bytes;
+    return RL_OK;
+}
+
+int rl_set_instrumented(rl_ctx* c, int enabled) {
+    if (!c) return RL_E_INVALID;
+    c->instrumented = enabled != 0;
+    return RL_OK;
+}
+
+int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
+    if (!c) return RL_E_INVALID;
+    c->has_scene = false;
+    FlatScene fs;
+    std::string err;
+    int rc = flatten_scene(scene, &fs, &err);
+    if (rc != RL_OK) return fail(c, rc, err);
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CK(c, cudaEventRecord(c->ev0, s));
+    CK(c, upload(c->prims, fs.prims, s));
+    CK(c, upload(c->tri_verts, fs.tri_verts, s));
+    CK(c, upload(c->tri_shade, fs.tri_shade, s));
+    CK(c, upload(c->xforms, fs.xforms, s));
+    CK(c, upload(c->spheres, fs.spheres, s));
+    CK(c, upload(c->quads, fs.quads, s));
+    CK(c, upload(c->sphere_node, fs.sphere_node, s));
+    CK(c, upload(c->quad_node, fs.quad_node, s));
+    CK(c, upload(c->materials, fs.materials, s));
+    CK(c, upload(c->textures, fs.textures, s));
+    CK(c, upload(c->lights, fs.lights, s));
+    // images
+    for (DevBuf& b : c->image_texels) b.release();
+    c->image_texels.assign(fs.images.size(), DevBuf());
+    std::vector<DevImage> dimg(fs.images.size());
+    size_t image_bytes = 0;
+    for (size_t i = 0; i < fs.images.size(); i++) {
+        CK(c, upload(c->image_texels[i], fs.images[i].texels, s));
+        dimg[i].texels = c->image_texels[i].as<float4>();
+        dimg[i].width = fs.images[i].w;
+        dimg[i].height = fs.images[i].h;
+        image_bytes += fs.images[i].texels.size() * sizeof(float4);
+    }
+    CK(c, upload(c->images, dimg, s));
+    // LBVH
+    int n = (int)fs.bvh_ref.size();
+    int nn = n >= 2 ? n - 1 : (n == 1 ? 1 : 0);
+    CK(c, upload(c->bvh_aabb, fs.bvh_aabb, s));
+    CK(c, upload(c->bvh_ref, fs.bvh_ref, s));
+    CK(c, upload(c->bvh_node_id, fs.bvh_node_id, s));
+    c->upload_launches = 0;
+    if (n > 0) {
+        CK(c, c->bounds.reserve(6 * sizeof(float)));
+        CK(c, c->keys.reserve(n * sizeof(uint64_t)));
+        CK(c, c->keys_tmp.reserve(n * sizeof(uint64_t)));
+        CK(c, c->sorted_prim.reserve(n * sizeof(int)));
+        CK(c, c->idx_tmp.reserve(n * sizeof(int)));
+        CK(c, c->left.reserve((size_t)nn * sizeof(int)));
+        CK(c, c->right.reserve((size_t)nn * sizeof(int)));
+        CK(c, c->parent.reserve((size_t)(2 * n) * sizeof(int)));
+        CK(c, c->node_aabb.reserve((size_t)nn * 6 * sizeof(float)));
+        CK(c, c->lbvh_counters.reserve((size_t)nn * sizeof(int)));
+        CK(c, c->nodes.reserve((size_t)nn * sizeof(BvhNode)));
+        LbvhBuffers lb;
+        lb.prim_aabb = c->bvh_aabb.as<float>();
+        lb.prim_ref = c->bvh_ref.as<int>();
+        lb.bounds = c->bounds.as<float>();
+        lb.keys = c->keys.as<uint64_t>();
+        lb.sorted_prim = c->sorted_prim.as<int>();
+        lb.keys_tmp = c->keys_tmp.as<uint64_t>();
+        lb.idx_tmp = c->idx_tmp.as<int>();
+        lb.left = c->left.as<int>();
+        lb.right = c->right.as<int>();
+        lb.parent = c->parent.as<int>();
+        lb.node_aabb = c->node_aabb.as<float>();
+        lb.counters = c->lbvh_counters.as<int>();
+        lb.nodes = c->nodes.as<BvhNode>();
+        CK(c, lbvh_build(lb, n, s, &c->upload_launches));
+    }
+    CK(c, cudaEventRecord(c->ev1, s));
+    CK(c, cudaStreamSynchronize(s));  // the host vectors die with this scope
+    CK(c, cudaEventElapsedTime(&c->upload_ms, c->ev0, c->ev1));
+
+    DevScene& d = c->ds;
+    d = DevScene{};
+    d.flavor = fs.flavor;
+    d.n_prims = (int)fs.prims.size();
+    d.n_tris = (int)fs.tri_verts.size();
+    d.n_spheres = (int)fs.spheres.size();
+    d.n_quads = (int)fs.quads.size();
+    d.n_bvh_prims = n;
+    d.n_bvh_nodes = nn;
+    d.n_materials = (int)fs.materials.size();
+    d.n_textures = (int)fs.textures.size();
+    d.n_lights = (int)fs.lights.size();
+    d.n_images = (int)fs.images.size();
+    d.n_xforms = (int)fs.xforms.size();
+    d.has_transparency = fs.has_transparency;
+    d.max_reflection_depth = fs.max_reflection_depth;
+    for (int k = 0; k < 3; k++) d.void_color[k] = fs.void_color[k];
+    d.prims = c->prims.as<RtcPrim>();
+    d.tri_verts = c->tri_verts.as<TriVerts>();
+    d.tri_shade = c->tri_shade.as<TriShade>();
+    d.xforms = c->xforms.as<Xform>();
+    d.spheres = c->spheres.as<OwSphere>();
+    d.quads = c->quads.as<OwQuad>();
+    d.sphere_node = c->sphere_node.as<int>();
+    d.quad_node = c->quad_node.as<int>();
+    d.materials = c->materials.as<DevMaterial>();
+    d.textures = c->textures.as<DevTexture>();
+    d.images = c->images.as<DevImage>();
+    d.lights = c->lights.as<DevLight>();
+    d.nodes = c->nodes.as<BvhNode>();
+
+    rl_scene_info& si = c->info;
+    si = rl_scene_info{};
+    si.flavor = fs.flavor;
+    si.n_prims = d.n_prims;
+    si.n_bvh_prims = n;
+    si.n_bvh_nodes = n >= 2 ? n - 1 : 0;
+    si.n_materials = d.n_materials;
+    si.n_textures = d.n_textures;
+    si.n_lights = d.n_lights;
+    si.has_transparency = d.has_transparency;
+    si.device_bytes = (int64_t)(fs.prims.size() * sizeof(RtcPrim) + fs.tri_verts.size() * (sizeof(TriVerts) + sizeof(TriShade)) +
+                                fs.spheres.size() * sizeof(OwSphere) + fs.quads.size() * sizeof(OwQuad) +
+                                (size_t)nn * sizeof(BvhNode) + image_bytes + fs.materials.size() * sizeof(DevMaterial));
+    c->has_scene = true;
+    return RL_OK;
+}
+
+int rl_scene_info_get(rl_ctx* c, rl_scene_info* out) {
+    if (!c || !out) return RL_E_INVALID;
+    if (!c->has_scene) return fail(c, RL_E_NO_SCENE, "no scene uploaded");
+    *out = c->info;
+    return RL_OK;
+}
+
+int rl_lbvh_download(rl_ctx* c, rl_lbvh_host* out) {
+    if (!c || !out) return RL_E_INVALID;
+    if (!c->has_scene) return fail(c, RL_E_NO_SCENE, "no scene uploaded");
+    int n = c->info.n_bvh_prims, m = c->info.n_bvh_nodes;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    auto dl = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
+        if (!dst || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, s);
+    };
+    if (n > 0) {
+        CK(c, dl(out->prim_aabb, c->bvh_aabb, (size_t)n * 6 * sizeof(float)));
+        CK(c, dl(out->prim_node, c->bvh_node_id, (size_t)n * sizeof(int)));
+        CK(c, dl(out->morton, c->keys, (size_t)n * sizeof(uint64_t)));
+        CK(c, dl(out->sorted_prim, c->sorted_prim, (size_t)n * sizeof(int)));
+        float b[6];
+        CK(c, cudaMemcpyAsync(b, c->bounds.p, sizeof(b), cudaMemcpyDeviceToHost, s));
+        CK(c, cudaStreamSynchronize(s));
+        for (int k = 0; k < 3; k++) {
+            out->scene_lo[k] = b[k];
+            out->scene_hi[k] = b[3 + k];
+        }
+    }
+    if (m > 0) {
+        CK(c, dl(out->left, c->left, (size_t)m * sizeof(int)));
+        CK(c, dl(out->right, c->right, (size_t)m * sizeof(int)));
+        CK(c, dl(out->parent, c->parent, (size_t)(m + n) * sizeof(int)));
+        CK(c, dl(out->node_aabb, c->node_aabb, (size_t)m * 6 * sizeof(float)));
+    }
+    CK(c, cudaStreamSynchronize(s));
+    return RL_OK;
+}
+
+}  // extern "C"
+
+// ---- job tables ------------------------------------------------------------------------------------------
+static int make_job_table(rl_ctx* c, const rl_job* jobs, int n_jobs, int width, int height, int n_chunks, bool ow,
+                          cudaStream_t s, JobTable* jt) {
+    if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(c, RL_E_INVALID, "bad job list");
+    std::vector<long long> prefix(n_jobs + 1, 0);
+    for (int i = 0; i < n_jobs; i++) {
+        const rl_job& j = jobs[i];
+        if (j.x0 < 0 || j.y0 < 0 || j.x1 > width || j.y1 > height || j.x0 >= j.x1 || j.y0 >= j.y1)
+            return fail(c, RL_E_INVALID, "job rectangle outside the image");
+        long long items = padded_pixels(j.x1 - j.x0, j.y1 - j.y0);
+        if (ow) {
+            if (j.chunk_begin < 0 || j.chunk_end > n_chunks || j.chunk_begin >= j.chunk_end)
+                return fail(c, RL_E_INVALID, "job chunk range outside [0, n_chunks)");
+            items *= (j.chunk_end - j.chunk_begin);
+        }
+        prefix[i + 1] = prefix[i] + items;
+    }
+    CK(c, c->jobs.reserve(sizeof(rl_job) * (size_t)(n_jobs > 0 ? n_jobs : 1)));
+    CK(c, c->prefix.reserve(sizeof(long long) * (size_t)(n_jobs + 1)));
+    if (n_jobs > 0) CK(c, cudaMemcpyAsync(c->jobs.p, jobs, sizeof(rl_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->prefix.p, prefix.data(), sizeof(long long) * (size_t)(n_jobs + 1), cudaMemcpyHostToDevice, s));
+    CK(c, cudaStreamSynchronize(s));  // `prefix` is a local
+    jt->jobs = c->jobs.as<rl_job>();
+    jt->prefix = c->prefix.as<long long>();
+    jt->n_jobs = n_jobs;
+    jt->n_items = prefix[n_jobs];
+    return RL_OK;
+}
+
+static int read_counters(rl_ctx* c, cudaStream_t s, rl_stats* st) {
+    Counters h;
+    CK(c, cudaMemcpyAsync(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    if (st) {
+        st->rays = h.rays;
+        st->node_visits = h.node_visits;
+        st->prim_tests = h.prim_tests;
+        st->tri_tests = h.tri_tests;
+        st->shades = h.shades;
+        st->overflow = h.overflow;
+    }
+    if (h.overflow) return fail(c, RL_E_OVERFLOW, "a traversal stack / work list overflowed on the device");
+    return RL_OK;
+}
+
+extern "C" {
+
+int rl_trace_batch(rl_ctx* c, const rl_ray* rays, uint64_t n, rl_hit* out) {
+    if (!c || (n > 0 && (!rays || !out))) return RL_E_INVALID;
+    if (!c->has_scene) return fail(c, RL_E_NO_SCENE, "no scene uploaded");
+    if (n == 0) return RL_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CK(c, c->rays.reserve(n * sizeof(rl_ray)));
+    CK(c, c->hits.reserve(n * sizeof(rl_hit)));
+    CK(c, cudaMemcpyAsync(c->rays.p, rays, n * sizeof(rl_ray), cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    if (c->ds.flavor == RL_FLAVOR_RTC)
+        CK(c, launch_rtc_trace(c->ds, c->rays.as<rl_ray>(), n, c->hits.as<rl_hit>(), c->counters.as<Counters>(), c->instrumented, s));
+    else
+        CK(c, launch_ow_trace(c->ds, c->rays.as<rl_ray>(), n, c->hits.as<rl_hit>(), c->counters.as<Counters>(), c->instrumented, s));
+    CK(c, cudaMemcpyAsync(out, c->hits.p, n * sizeof(rl_hit), cudaMemcpyDeviceToHost, s));
+    return read_counters(c, s, nullptr);
+}
+
+int rl_render_rtc_device(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, const rl_job* jobs, int32_t n_jobs,
+                         void* d_out_rgb, void* stream, rl_stats* stats) {
+    if (!c || !cam || !d_out_rgb) return RL_E_INVALID;
+    if (!c->has_scene || c->ds.flavor != RL_FLAVOR_RTC) return fail(c, RL_E_NO_SCENE, "no RTC scene uploaded");
+    if (aa < 1) return fail(c, RL_E_INVALID, "anti_aliasing_samples must be >= 1");
+    if (cam->hsize < 1 || cam->vsize < 1) return fail(c, RL_E_INVALID, "empty image");
+    double inv[12];
+    std::string err;
+    if (!invert_affine_4x4(cam->transform, inv, &err)) return fail(c, RL_E_INVALID, err);
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    JobTable jt;
+    int rc = make_job_table(c, jobs, n_jobs, cam->hsize, cam->vsize, 1, false, s, &jt);
+    if (rc != RL_OK) return rc;
+    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    CK(c, cudaEventRecord(c->ev0, s));
+    CK(c, launch_rtc_render(c->ds, cam, inv, aa, jt, (float*)d_out_rgb, c->counters.as<Counters>(), c->instrumented, s));
+    CK(c, cudaEventRecord(c->ev1, s));
+    rl_stats st{};
+    rc = read_counters(c, s, &st);
+    float ms = 0.0f;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    st.kernel_ms = ms;
+    st.upload_ms = c->upload_ms;
+    st.kernel_launches = jt.n_items > 0 ? 1 : 0;
+    long long px = 0;
+    for (int i = 0; i < n_jobs; i++) px += (long long)(jobs[i].x1 - jobs[i].x0) * (jobs[i].y1 - jobs[i].y0);
+    st.samples = (uint64_t)px * aa * aa;
+    if (stats) *stats = st;
+    return rc;
+}
+
+int rl_render_rtc(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, float* out_rgb, rl_stats* stats) {
+    if (!c || !cam || !out_rgb) return RL_E_INVALID;
+    if (cam->hsize < 1 || cam->vsize < 1) return fail(c, RL_E_INVALID, "empty image");
+    size_t bytes = (size_t)cam->hsize * cam->vsize * 3 * sizeof(float);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->frame.reserve(bytes));
+    rl_job job{0, 0, cam->hsize, cam->vsize, 0, 1};
+    int rc = rl_render_rtc_device(c, cam, aa, &job, 1, c->frame.p, nullptr, stats);
+    if (rc != RL_OK) return rc;
+    CK(c, cudaMemcpyAsync(out_rgb, c->frame.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RL_OK;
+}
+
+int rl_ow_image_height(const rl_ow_camera* cam) { return cam ? ow_image_height(cam) : 0; }
+int rl_ow_num_chunks(const rl_ow_camera* cam) { return cam ? ow_num_chunks(cam->samples_per_pixel) : 0; }
+
+int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs, int32_t n_jobs,
+                        void* d_partial, void* stream, rl_stats* stats) {
+    if (!c || !cam || !d_partial) return RL_E_INVALID;
+    if (!c->has_scene || c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_NO_SCENE, "no OW scene uploaded");
+    if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0))
+        return fail(c, RL_E_INVALID, "bad camera parameters");
+    if (cam->max_depth < 0) return fail(c, RL_E_INVALID, "max_depth must be >= 0");
+    double dx = cam->lookfrom[0] - cam->lookat[0], dy = cam->lookfrom[1] - cam->lookat[1], dz = cam->lookfrom[2] - cam->lookat[2];
+    if (dx * dx + dy * dy + dz * dz <= 1e-16) return fail(c, RL_E_INVALID, "cannot normalize vector with magnitude 0");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
+    JobTable jt;
+    int rc = make_job_table(c, jobs, n_jobs, cam->image_width, H, nc, true, s, &jt);
+    if (rc != RL_OK) return rc;
+    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    CK(c, cudaEventRecord(c->ev0, s));
+    CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
+                           c->counters.as<Counters>(), c->instrumented, c->sm_count, s));
+    CK(c, cudaEventRecord(c->ev1, s));
+    rl_stats st{};
+    rc = read_counters(c, s, &st);
+    float ms = 0.0f;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    st.kernel_ms = ms;
+    st.upload_ms = c->upload_ms;
+    st.kernel_launches = jt.n_items > 0 ? 1 : 0;
+    uint64_t samples = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        uint64_t px = (uint64_t)(jobs[i].x1 - jobs[i].x0) * (uint64_t)(jobs[i].y1 - jobs[i].y0);
+        for (int ck = jobs[i].chunk_begin; ck < jobs[i].chunk_end; ck++) {
+            long long s0 = ((long long)ck * cam->samples_per_pixel) / nc, s1 = ((long long)(ck + 1) * cam->samples_per_pixel) / nc;
+            samples += px * (uint64_t)(s1 - s0);
+        }
+    }
+    st.samples = samples;
+    if (stats) *stats = st;
+    return rc;
+}
+
+int rl_ow_reduce_device(rl_ctx* c, const rl_ow_camera* cam, const void* d_partial, void* d_out, void* stream) {
+    if (!c || !cam || !d_partial || !d_out) return RL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CK(c, launch_ow_reduce(cam, (const float*)d_partial, (float*)d_out, s));
+    return RL_OK;
+}
+
+int rl_render_ow(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, float* out_rgb_sum, rl_stats* stats) {
+    if (!c || !cam || !out_rgb_sum) return RL_E_INVALID;
+    if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0))
+        return fail(c, RL_E_INVALID, "bad camera parameters");
+    int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
+    size_t frame = (size_t)cam->image_width * H * 3 * sizeof(float);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->partial.reserve(frame * nc));
+    CK(c, c->frame.reserve(frame));
+    rl_job job{0, 0, cam->image_width, H, 0, nc};
+    rl_stats st{};
+    int rc = rl_render_ow_device(c, cam, first_sample, &job, 1, c->partial.p, nullptr, &st);
+    if (rc != RL_OK) return rc;
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    rc = rl_ow_reduce_device(c, cam, c->partial.p, c->frame.p, nullptr);
+    if (rc != RL_OK) return rc;
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    CK(c, cudaMemcpyAsync(out_rgb_sum, c->frame.p, frame, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.0f;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    st.kernel_ms += ms;
+    st.kernel_launches += 1;
+    if (stats) *stats = st;
+    return RL_OK;
+}
+
+}  // extern "C"

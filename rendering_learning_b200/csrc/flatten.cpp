@@ -1,0 +1,516 @@
+// Scene flattener: lowers the reference's object tree (rl_scene_desc) to the SoA device layout.
+//
+//  * RTC: every leaf gets ONE composed, pre-inverted affine transform
+//         inv_total = inv_leaf * ... * inv_root   (Transformed::intersect, RTC/src/scene/object/transformed.rs:39-51,
+//         applies inv per nesting level; the normal matrix is inv_total^T — proved equivalent by the
+//         reference's own test at transformed.rs:226-278).  Triangles are baked to world space
+//         (t is preserved because ray directions are never renormalised, ray.rs:18-20).
+//         Group / Bounded only order or skip work and are flattened away (group.rs:29-42, bounded.rs:146-152).
+//  * OW : Transform (3x3 rotate / uniform scale) and Translate chains are baked into world-space
+//         triangles, quads and spheres (hittable/transform.rs:145-164, translate.rs:14-21); Bvh / list
+//         nodes are replaced by one LBVH over all bounded primitives (closest-hit semantics, bvh.rs:81-90).
+//
+// All composition / inversion is done in f64 and rounded to f32 once, at the end.
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "scene.h"
+
+namespace rl {
+namespace {
+
+struct Aff {  // 3x4 affine, f64
+    double m[3][4];
+};
+Aff aff_identity() {
+    Aff a{};
+    a.m[0][0] = a.m[1][1] = a.m[2][2] = 1.0;
+    return a;
+}
+Aff aff_mul(const Aff& a, const Aff& b) {  // a * b
+    Aff r{};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 4; j++) {
+            double s = 0.0;
+            for (int k = 0; k < 3; k++) s += a.m[i][k] * b.m[k][j];
+            if (j == 3) s += a.m[i][3];
+            r.m[i][j] = s;
+        }
+    }
+    return r;
+}
+// inverse of an affine map [A | t]: [A^-1 | -A^-1 t], A^-1 by the adjugate
+bool aff_inverse(const Aff& a, Aff* out) {
+    const double(*m)[4] = a.m;
+    double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+    double c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2];
+    double c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+    double det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02;
+    if (det == 0.0 || !std::isfinite(det)) return false;
+    double id = 1.0 / det;
+    double inv[3][3];
+    inv[0][0] = c00 * id;
+    inv[1][0] = c01 * id;
+    inv[2][0] = c02 * id;
+    inv[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id;
+    inv[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id;
+    inv[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id;
+    inv[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+    inv[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+    inv[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) out->m[i][j] = inv[i][j];
+        out->m[i][3] = -(inv[i][0] * m[0][3] + inv[i][1] * m[1][3] + inv[i][2] * m[2][3]);
+    }
+    return true;
+}
+bool aff_from_4x4(const double* p, Aff* out, std::string* err) {
+    if (p[12] != 0.0 || p[13] != 0.0 || p[14] != 0.0 || p[15] != 1.0) {
+        *err = "projective 4x4 transform (bottom row != 0 0 0 1) is not supported";
+        return false;
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++) out->m[i][j] = p[i * 4 + j];
+    return true;
+}
+void aff_point(const Aff& a, const double p[3], double o[3]) {
+    for (int i = 0; i < 3; i++) o[i] = a.m[i][0] * p[0] + a.m[i][1] * p[1] + a.m[i][2] * p[2] + a.m[i][3];
+}
+void aff_vec(const Aff& a, const double p[3], double o[3]) {
+    for (int i = 0; i < 3; i++) o[i] = a.m[i][0] * p[0] + a.m[i][1] * p[1] + a.m[i][2] * p[2];
+}
+// n_world = inv^T * n_local
+void aff_normal(const Aff& inv, const double n[3], double o[3]) {
+    for (int i = 0; i < 3; i++) o[i] = inv.m[0][i] * n[0] + inv.m[1][i] * n[1] + inv.m[2][i] * n[2];
+}
+void store_rows(const Aff& a, float4 r[3]) {
+    for (int i = 0; i < 3; i++) r[i] = make_float4((float)a.m[i][0], (float)a.m[i][1], (float)a.m[i][2], (float)a.m[i][3]);
+}
+inline float as_f(int v) {
+    float f;
+    std::memcpy(&f, &v, 4);
+    return f;
+}
+bool normalize3(double v[3]) {
+    double m = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (!(m > 0.0)) return false;
+    v[0] /= m; v[1] /= m; v[2] /= m;
+    return true;
+}
+
+// conservative f32 box around f64 extents (so rounding to f32 never shrinks a box)
+void push_aabb(FlatScene* fs, const double lo[3], const double hi[3], int ref, int node) {
+    for (int k = 0; k < 3; k++) {
+        float f = (float)lo[k];
+        if ((double)f > lo[k]) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+        // thin / touching geometry: pad by 4 ulp so slab tests stay conservative in f32
+        float pad = 4.0f * 1.1920929e-7f * std::fmax(std::fabs(f), 1e-3f);
+        fs->bvh_aabb.push_back(f - pad);
+    }
+    for (int k = 0; k < 3; k++) {
+        float f = (float)hi[k];
+        if ((double)f < hi[k]) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+        float pad = 4.0f * 1.1920929e-7f * std::fmax(std::fabs(f), 1e-3f);
+        fs->bvh_aabb.push_back(f + pad);
+    }
+    fs->bvh_ref.push_back(ref);
+    fs->bvh_node_id.push_back(node);
+}
+
+struct Flattener {
+    const rl_scene_desc* d;
+    FlatScene* fs;
+    std::string* err;
+    int rc = RL_OK;
+
+    bool fail(int code, const std::string& msg) {
+        if (rc == RL_OK) {
+            rc = code;
+            *err = msg;
+        }
+        return false;
+    }
+    bool check_node(int id) {
+        if (id < 0 || id >= d->n_nodes) return fail(RL_E_INVALID, "node id out of range");
+        return true;
+    }
+    const double* params(const rl_node& nd, int need) {
+        if (nd.param < 0 || (int64_t)nd.param + need > d->n_params) {
+            fail(RL_E_INVALID, "node params out of range");
+            return nullptr;
+        }
+        return d->params + nd.param;
+    }
+
+    // ---- materials / textures ------------------------------------------------------------------
+    bool lower_tables() {
+        for (int i = 0; i < d->n_textures; i++) {
+            const rl_texture& t = d->textures[i];
+            DevTexture o{};
+            o.a = make_float4((float)t.a[0], (float)t.a[1], (float)t.a[2], as_f(t.kind));
+            float inv_scale = t.kind == RL_TEX_OW_CHECKER ? (float)(1.0 / t.scale) : 0.0f;
+            o.b = make_float4((float)t.b[0], (float)t.b[1], (float)t.b[2], inv_scale);
+            o.idx = make_int4(t.tex_a, t.tex_b, t.image, 0);
+            if (t.kind == RL_TEX_OW_CHECKER &&
+                (t.tex_a < 0 || t.tex_a >= d->n_textures || t.tex_b < 0 || t.tex_b >= d->n_textures))
+                return fail(RL_E_INVALID, "checker sub-texture out of range");
+            if (t.kind == RL_TEX_OW_IMAGE && (t.image < 0 || t.image >= d->n_images))
+                return fail(RL_E_INVALID, "image index out of range");
+            fs->textures.push_back(o);
+        }
+        for (int i = 0; i < d->n_images; i++) {
+            const rl_image& im = d->images[i];
+            if (im.width <= 0 || im.height <= 0 || !im.rgb) return fail(RL_E_INVALID, "Image has no data");
+            FlatScene::Img o;
+            o.w = im.width;
+            o.h = im.height;
+            o.texels.resize((size_t)im.width * im.height);
+            for (size_t k = 0; k < o.texels.size(); k++)
+                o.texels[k] = make_float4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 0.0f);
+            fs->images.push_back(std::move(o));
+        }
+        for (int i = 0; i < d->n_materials; i++) {
+            const rl_material& m = d->materials[i];
+            DevMaterial o{};
+            if (m.texture >= d->n_textures) return fail(RL_E_INVALID, "material texture out of range");
+            o.color = make_float4((float)m.color[0], (float)m.color[1], (float)m.color[2], as_f(m.texture));
+            if (m.kind == RL_MAT_RTC_PHONG) {
+                o.a = make_float4((float)m.ambient, (float)m.diffuse, (float)m.specular, (float)m.shininess);
+                o.b = make_float4((float)m.reflectivity, (float)m.transparency, (float)m.refractive_index,
+                                  as_f(m.kind));
+                if (m.transparency > 0.0) fs->has_transparency = 1;
+            } else {
+                o.a = make_float4((float)m.fuzz, (float)m.refractive_index, 0.0f, 0.0f);
+                o.b = make_float4(0.0f, 0.0f, 0.0f, as_f(m.kind));
+                if ((m.kind == RL_MAT_OW_LAMBERTIAN || m.kind == RL_MAT_OW_DIFFUSE_LIGHT) && m.texture < 0)
+                    return fail(RL_E_INVALID, "OW material without a texture");
+            }
+            fs->materials.push_back(o);
+        }
+        for (int i = 0; i < d->n_lights; i++) {
+            const rl_light& l = d->lights[i];
+            DevLight o;
+            o.pos = make_float4((float)l.position[0], (float)l.position[1], (float)l.position[2], 0.0f);
+            o.intensity = make_float4((float)l.intensity[0], (float)l.intensity[1], (float)l.intensity[2], 0.0f);
+            fs->lights.push_back(o);
+        }
+        return true;
+    }
+
+    bool check_material(int m) {
+        if (m < 0 || m >= d->n_materials) return fail(RL_E_INVALID, "material index out of range");
+        return true;
+    }
+
+    // world -> pattern space for a leaf whose material has a pattern (pattern.inv * inv_total)
+    bool pattern_xform(int material, const Aff& inv_total, Aff* out, bool* has) {
+        int tex = d->materials[material].texture;
+        *has = false;
+        *out = inv_total;
+        if (tex < 0) return true;
+        Aff fwd, pinv;
+        if (!aff_from_4x4(d->textures[tex].transform, &fwd, err)) return fail(RL_E_UNSUPPORTED, *err);
+        if (!aff_inverse(fwd, &pinv)) return fail(RL_E_INVALID, "Matrix is not invertible.");
+        *out = aff_mul(pinv, inv_total);
+        *has = true;
+        return true;
+    }
+
+    // ---- RTC -----------------------------------------------------------------------------------
+    // fwd_total: object -> world, inv_total: world -> object
+    bool rtc_node(int id, const Aff& fwd_total, const Aff& inv_total, int depth) {
+        if (!check_node(id)) return false;
+        if (depth > 64) return fail(RL_E_INVALID, "object tree too deep (cycle?)");
+        const rl_node& nd = d->nodes[id];
+        switch (nd.kind) {
+            case RL_RTC_SPHERE: case RL_RTC_PLANE: case RL_RTC_CUBE: case RL_RTC_CYLINDER: case RL_RTC_CONE: {
+                if (!check_material(nd.material)) return false;
+                RtcPrim p{};
+                store_rows(inv_total, p.inv);
+                store_rows(fwd_total, p.fwd);
+                Aff pat;
+                bool has;
+                if (!pattern_xform(nd.material, aff_identity(), &pat, &has)) return false;
+                store_rows(pat, p.pat);
+                p.ymin = -INFINITY;
+                p.ymax = INFINITY;
+                if (nd.kind == RL_RTC_CYLINDER || nd.kind == RL_RTC_CONE) {
+                    const double* q = params(nd, 2);
+                    if (!q) return false;
+                    p.ymin = (float)q[0];
+                    p.ymax = (float)q[1];
+                }
+                p.kind = nd.kind == RL_RTC_SPHERE ? PK_RTC_SPHERE : nd.kind == RL_RTC_PLANE ? PK_RTC_PLANE
+                       : nd.kind == RL_RTC_CUBE ? PK_RTC_CUBE : nd.kind == RL_RTC_CYLINDER ? PK_RTC_CYLINDER
+                                                                                            : PK_RTC_CONE;
+                p.flags = nd.flags & 1;
+                p.material = nd.material;
+                p.node = id;
+                fs->prims.push_back(p);
+                return true;
+            }
+            case RL_RTC_TRIANGLE: {
+                if (!check_material(nd.material)) return false;
+                const double* q = params(nd, 18);
+                if (!q) return false;
+                double P[3][3], N[3][3];
+                for (int k = 0; k < 3; k++) aff_point(fwd_total, q + 3 * k, P[k]);
+                bool smooth = nd.flags & 1;
+                if (smooth) {
+                    // normalize(inv^T * normalize(sum b_i n_i)) == normalize(sum b_i (inv^T n_i))
+                    for (int k = 0; k < 3; k++) aff_normal(inv_total, q + 9 + 3 * k, N[k]);
+                } else {
+                    // Triangle::flat (triangle.rs:30-42): normal = normalize(e2 x e1) in object space
+                    double e1[3], e2[3], n[3];
+                    for (int k = 0; k < 3; k++) { e1[k] = q[3 + k] - q[k]; e2[k] = q[6 + k] - q[k]; }
+                    n[0] = e2[1] * e1[2] - e2[2] * e1[1];
+                    n[1] = e2[2] * e1[0] - e2[0] * e1[2];
+                    n[2] = e2[0] * e1[1] - e2[1] * e1[0];
+                    if (!normalize3(n)) return fail(RL_E_INVALID, "degenerate triangle cannot be normalized");
+                    aff_normal(inv_total, n, N[0]);
+                    if (!normalize3(N[0])) return fail(RL_E_INVALID, "degenerate triangle normal");
+                    for (int k = 0; k < 3; k++) N[1][k] = N[2][k] = N[0][k];
+                }
+                Aff pat;
+                bool has;
+                if (!pattern_xform(nd.material, inv_total, &pat, &has)) return false;
+                int xf = 0;
+                if (has) {
+                    Xform x;
+                    store_rows(pat, x.r);
+                    fs->xforms.push_back(x);
+                    xf = (int)fs->xforms.size();  // index + 1
+                }
+                push_triangle(P, N, nullptr, nd.material, id, (smooth ? 1 : 0) | (xf << 8));
+                return true;
+            }
+            case RL_RTC_TRANSFORMED: {
+                const double* q = params(nd, 16);
+                if (!q) return false;
+                Aff fwd, inv;
+                if (!aff_from_4x4(q, &fwd, err)) return fail(RL_E_UNSUPPORTED, *err);
+                if (!aff_inverse(fwd, &inv)) return fail(RL_E_INVALID, "Matrix is not invertible.");
+                return rtc_node(nd.child_begin, aff_mul(fwd_total, fwd), aff_mul(inv, inv_total), depth + 1);
+            }
+            case RL_RTC_GROUP: {
+                if (nd.child_begin < 0 || nd.child_end > d->n_children || nd.child_begin > nd.child_end)
+                    return fail(RL_E_INVALID, "group children out of range");
+                for (int k = nd.child_begin; k < nd.child_end; k++)
+                    if (!rtc_node(d->children[k], fwd_total, inv_total, depth + 1)) return false;
+                return true;
+            }
+            case RL_RTC_BOUNDED:
+                return rtc_node(nd.child_begin, fwd_total, inv_total, depth + 1);
+            case RL_RTC_CSG:
+                return fail(RL_E_UNSUPPORTED, "Csg objects are not lowered to the device yet (SURVEY.md §8f)");
+            default:
+                return fail(RL_E_INVALID, "unknown RTC node kind");
+        }
+    }
+
+    void push_triangle(const double P[3][3], const double N[3][3], const double* uv, int material, int node,
+                       int flags) {
+        TriVerts v;
+        v.p0 = make_float4((float)P[0][0], (float)P[0][1], (float)P[0][2], as_f(material));
+        v.p1 = make_float4((float)P[1][0], (float)P[1][1], (float)P[1][2], as_f(node));
+        v.p2 = make_float4((float)P[2][0], (float)P[2][1], (float)P[2][2], as_f(flags));
+        TriShade s;
+        double u[6] = {0, 0, 0, 0, 0, 0};
+        if (uv) std::memcpy(u, uv, sizeof(u));
+        s.s0 = make_float4((float)N[0][0], (float)N[0][1], (float)N[0][2], (float)u[0]);
+        s.s1 = make_float4((float)N[1][0], (float)N[1][1], (float)N[1][2], (float)u[1]);
+        s.s2 = make_float4((float)N[2][0], (float)N[2][1], (float)N[2][2], (float)u[2]);
+        s.s3 = make_float4((float)u[3], (float)u[4], (float)u[5], 0.0f);
+        int idx = (int)fs->tri_verts.size();
+        fs->tri_verts.push_back(v);
+        fs->tri_shade.push_back(s);
+        double lo[3], hi[3];
+        for (int k = 0; k < 3; k++) {
+            // bound the f32-rounded vertices the device will actually intersect
+            float a = (&v.p0.x)[k], b = (&v.p1.x)[k], c = (&v.p2.x)[k];
+            lo[k] = std::fmin(a, std::fmin(b, c));
+            hi[k] = std::fmax(a, std::fmax(b, c));
+        }
+        push_aabb(fs, lo, hi, make_ref(REF_TRI, idx), node);
+    }
+
+    // ---- OW ------------------------------------------------------------------------------------
+    // M: object -> world linear part + offset (p_world = M p + t); s = uniform scale factor of M
+    bool ow_node(int id, const Aff& fwd, const Aff& inv, bool rotated, int depth) {
+        if (!check_node(id)) return false;
+        if (depth > 64) return fail(RL_E_INVALID, "hittable tree too deep (cycle?)");
+        const rl_node& nd = d->nodes[id];
+        switch (nd.kind) {
+            case RL_OW_SPHERE: {
+                if (!check_material(nd.material)) return false;
+                const double* q = params(nd, 7);
+                if (!q) return false;
+                double c1[3], c2[3];
+                aff_point(fwd, q, c1);
+                aff_point(fwd, q + 3, c2);
+                // Transform only offers rotations and uniform scale, so a sphere stays a sphere
+                double sx = std::sqrt(fwd.m[0][0] * fwd.m[0][0] + fwd.m[1][0] * fwd.m[1][0] + fwd.m[2][0] * fwd.m[2][0]);
+                double r = q[6] * sx;
+                const rl_material& m = d->materials[nd.material];
+                if (rotated && m.texture >= 0 && texture_uses_uv(m.texture))
+                    return fail(RL_E_UNSUPPORTED, "image-textured sphere under a rotation is not lowered yet");
+                OwSphere s;
+                s.c = make_float4((float)c1[0], (float)c1[1], (float)c1[2], (float)r);
+                bool moving = nd.flags & 1;
+                s.dc = make_float4(moving ? (float)(c2[0] - c1[0]) : 0.0f, moving ? (float)(c2[1] - c1[1]) : 0.0f,
+                                   moving ? (float)(c2[2] - c1[2]) : 0.0f, as_f(nd.material));
+                int idx = (int)fs->spheres.size();
+                fs->spheres.push_back(s);
+                fs->sphere_node.push_back(id);
+                // swept bounds (sphere.rs:77-87), from the f32 values the device uses
+                double lo[3], hi[3];
+                double ar = std::fabs((double)s.c.w);
+                for (int k = 0; k < 3; k++) {
+                    double a = (&s.c.x)[k], b = a + (&s.dc.x)[k];
+                    lo[k] = std::fmin(a, b) - ar;
+                    hi[k] = std::fmax(a, b) + ar;
+                }
+                push_aabb(fs, lo, hi, make_ref(REF_SPHERE, idx), id);
+                return true;
+            }
+            case RL_OW_QUAD: {
+                if (!check_material(nd.material)) return false;
+                const double* q = params(nd, 9);
+                if (!q) return false;
+                double Q[3], U[3], V[3];
+                aff_point(fwd, q, Q);
+                aff_vec(fwd, q + 3, U);
+                aff_vec(fwd, q + 6, V);
+                double n[3] = {U[1] * V[2] - U[2] * V[1], U[2] * V[0] - U[0] * V[2], U[0] * V[1] - U[1] * V[0]};
+                double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+                if (!(nn > 1e-16)) return fail(RL_E_INVALID, "Failed to find normal because u and v were parallel");
+                double un[3] = {n[0], n[1], n[2]};
+                normalize3(un);
+                OwQuad o;
+                o.q = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)(un[0] * Q[0] + un[1] * Q[1] + un[2] * Q[2]));
+                o.u = make_float4((float)U[0], (float)U[1], (float)U[2], as_f(nd.material));
+                o.v = make_float4((float)V[0], (float)V[1], (float)V[2], 0.0f);
+                o.n = make_float4((float)un[0], (float)un[1], (float)un[2], 0.0f);
+                o.w = make_float4((float)(n[0] / nn), (float)(n[1] / nn), (float)(n[2] / nn), 0.0f);
+                int idx = (int)fs->quads.size();
+                fs->quads.push_back(o);
+                fs->quad_node.push_back(id);
+                double lo[3], hi[3];
+                for (int k = 0; k < 3; k++) {
+                    double c[4] = {Q[k], Q[k] + U[k], Q[k] + V[k], Q[k] + U[k] + V[k]};
+                    lo[k] = std::fmin(std::fmin(c[0], c[1]), std::fmin(c[2], c[3]));
+                    hi[k] = std::fmax(std::fmax(c[0], c[1]), std::fmax(c[2], c[3]));
+                }
+                push_aabb(fs, lo, hi, make_ref(REF_QUAD, idx), id);
+                return true;
+            }
+            case RL_OW_TRIANGLE: {
+                if (!check_material(nd.material)) return false;
+                const double* q = params(nd, 24);
+                if (!q) return false;
+                double P[3][3], N[3][3];
+                for (int k = 0; k < 3; k++) aff_point(fwd, q + 3 * k, P[k]);
+                bool has_uv = nd.flags & 1, has_n = nd.flags & 2;
+                if (has_n) {
+                    for (int k = 0; k < 3; k++) aff_normal(inv, q + 15 + 3 * k, N[k]);
+                } else {
+                    // Plane::new (flat/plane.rs:23-28): n = normalize(u x v)
+                    double u[3], v[3], n[3];
+                    for (int k = 0; k < 3; k++) { u[k] = P[1][k] - P[0][k]; v[k] = P[2][k] - P[0][k]; }
+                    n[0] = u[1] * v[2] - u[2] * v[1];
+                    n[1] = u[2] * v[0] - u[0] * v[2];
+                    n[2] = u[0] * v[1] - u[1] * v[0];
+                    if (!normalize3(n)) return fail(RL_E_INVALID, "Failed to find normal because u and v were parallel");
+                    for (int k = 0; k < 3; k++) N[0][k] = N[1][k] = N[2][k] = n[k];
+                }
+                push_triangle(P, N, has_uv ? q + 9 : nullptr, nd.material, id, (has_n ? 1 : 0) | (has_uv ? 2 : 0));
+                return true;
+            }
+            case RL_OW_TRANSFORM: {
+                const double* q = params(nd, 18);
+                if (!q) return false;
+                Aff m{}, mi{};
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) { m.m[i][j] = q[i * 3 + j]; mi.m[i][j] = q[9 + i * 3 + j]; }
+                bool rot = rotated || m.m[0][1] != 0.0 || m.m[0][2] != 0.0 || m.m[1][0] != 0.0 ||
+                           m.m[1][2] != 0.0 || m.m[2][0] != 0.0 || m.m[2][1] != 0.0;
+                return ow_node(nd.child_begin, aff_mul(fwd, m), aff_mul(mi, inv), rot, depth + 1);
+            }
+            case RL_OW_TRANSLATE: {
+                const double* q = params(nd, 3);
+                if (!q) return false;
+                Aff m = aff_identity(), mi = aff_identity();
+                for (int i = 0; i < 3; i++) { m.m[i][3] = q[i]; mi.m[i][3] = -q[i]; }
+                return ow_node(nd.child_begin, aff_mul(fwd, m), aff_mul(mi, inv), rotated, depth + 1);
+            }
+            case RL_OW_BVH:
+            case RL_OW_LIST: {
+                if (nd.child_begin < 0 || nd.child_end > d->n_children || nd.child_begin > nd.child_end)
+                    return fail(RL_E_INVALID, "children out of range");
+                if (nd.kind == RL_OW_BVH && nd.child_begin == nd.child_end)
+                    return fail(RL_E_INVALID, "Cannot make a BVH node without hittables.");
+                for (int k = nd.child_begin; k < nd.child_end; k++)
+                    if (!ow_node(d->children[k], fwd, inv, rotated, depth + 1)) return false;
+                return true;
+            }
+            default:
+                return fail(RL_E_INVALID, "unknown OW node kind");
+        }
+    }
+
+    bool texture_uses_uv(int tex) {
+        const rl_texture& t = d->textures[tex];
+        if (t.kind == RL_TEX_OW_IMAGE) return true;
+        if (t.kind == RL_TEX_OW_CHECKER) return texture_uses_uv(t.tex_a) || texture_uses_uv(t.tex_b);
+        return false;
+    }
+};
+
+}  // namespace
+
+// inverse of an affine 4x4 (row-major) as 3x4 rows — used for the RTC camera (Camera::transform.inverse())
+bool invert_affine_4x4(const double* m16, double* inv12, std::string* err) {
+    Aff fwd, inv;
+    if (!aff_from_4x4(m16, &fwd, err)) return false;
+    if (!aff_inverse(fwd, &inv)) {
+        *err = "Matrix is not invertible.";
+        return false;
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++) inv12[i * 4 + j] = inv.m[i][j];
+    return true;
+}
+
+int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err) {
+    if (!d || d->abi_version != RL_B200_ABI_VERSION) {
+        *err = "scene description missing or ABI version mismatch";
+        return RL_E_INVALID;
+    }
+    if (d->flavor != RL_FLAVOR_RTC && d->flavor != RL_FLAVOR_OW) {
+        *err = "unknown scene flavor";
+        return RL_E_INVALID;
+    }
+    Flattener f{d, out, err};
+    out->flavor = d->flavor;
+    out->max_reflection_depth = d->max_reflection_depth;
+    for (int k = 0; k < 3; k++) out->void_color[k] = (float)d->void_color[k];
+    if (!f.lower_tables()) return f.rc;
+    if (d->flavor == RL_FLAVOR_RTC) {
+        if (d->max_reflection_depth < 0 || d->max_reflection_depth > 16) {
+            *err = "max_reflection_depth must be in [0, 16] on the device path";
+            return RL_E_UNSUPPORTED;
+        }
+        for (int k = 0; k < d->n_roots; k++)
+            if (!f.rtc_node(d->roots[k], aff_identity(), aff_identity(), 0)) return f.rc;
+    } else {
+        if (d->n_roots != 1) {
+            *err = "an OW scene has exactly one root hittable";
+            return RL_E_INVALID;
+        }
+        if (!f.ow_node(d->roots[0], aff_identity(), aff_identity(), false, 0)) return f.rc;
+    }
+    return RL_OK;
+}
+
+}  // namespace rl

@@ -1,0 +1,506 @@
+// OW (ray-tracing-one-weekend) render path: stochastic path tracer in f32.
+//
+// Replaces Camera::_render -> get_ray -> ray_color -> world.hit / Material::scatter / emitted
+// (OW/src/camera.rs:145-260, bvh.rs:81-90, hittable/*.rs, material.rs:69-195, texture.rs:15-82).
+//
+// Execution model: persistent warps.  A work item is (pixel, sample chunk); every LANE owns one item at a
+// time, walks its samples in order (so the per-item sum is deterministic) and regenerates a new camera
+// path as soon as its current path dies, so lanes never idle behind a long path in the same warp.  Lanes
+// that run out of samples refill from a global queue with one warp-aggregated atomic (ballot + popc
+// compaction of the requesting lanes).  Partial sums are written per (chunk, pixel) with plain stores and
+// folded in chunk order by k_ow_reduce, so the image is bit-identical for any GPU count / schedule.
+//
+// RNG: Philox4x32-10 keyed by the camera seed, counter = (pixel, absolute sample, bounce, dimension) —
+// statistical parity with the reference's ChaCha8 streams, and absolute sample indices
+// keep render_from_checkpoint streams disjoint like camera.rs:162-170.
+#include "device.cuh"
+#include "kernels.h"
+
+namespace rl {
+namespace {
+
+struct OwCam {
+    int width, height, spp, max_depth;
+    int first_sample, n_chunks, defocus, pad;
+    float3 lookfrom, pixel00, du, dv, disk_u, disk_v, background;
+    unsigned seed_lo, seed_hi;
+};
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// uniform point on the unit sphere (any unbiased sampler gives statistical parity with UnitSphere)
+__device__ __forceinline__ float3 unit_vector(float u1, float u2) {
+    float z = 1.0f - 2.0f * u1;
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return f3(r * c, r * s, z);
+}
+
+// ---- textures (texture.rs) -------------------------------------------------------------------------------
+__device__ __forceinline__ float3 tex_value(const DevScene& sc, int tex, float u, float v, float3 p) {
+    DevTexture t = sc.textures[tex];
+    for (int guard = 0; guard < 8 && __float_as_int(t.a.w) == RL_TEX_OW_CHECKER; guard++) {
+        float inv_scale = t.b.w;  // texture.rs:42-54
+        long long xi = (long long)floorf(p.x * inv_scale);
+        long long yi = (long long)floorf(p.y * inv_scale);
+        long long zi = (long long)floorf(p.z * inv_scale);
+        bool even = ((xi + yi + zi) % 2) == 0;
+        t = sc.textures[even ? t.idx.x : t.idx.y];
+    }
+    if (__float_as_int(t.a.w) == RL_TEX_OW_IMAGE) {  // texture.rs:63-81
+        DevImage im = sc.images[t.idx.z];
+        float uu = fminf(fmaxf(u, 0.0f), 1.0f);
+        float vv = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+        int i = (int)(uu * (float)(im.width - 1));
+        int j = (int)(vv * (float)(im.height - 1));
+        float4 px = __ldg(im.texels + (size_t)j * im.width + i);
+        return f3(px);
+    }
+    return f3(t.a);
+}
+
+struct OwHit {
+    float t;
+    int ref;  // leaf ref, -1 none
+    float b1, b2;
+};
+
+// world.hit(r, [tmin, inf)) through the LBVH.  `self_ref` is the primitive the ray starts on.
+template <bool COUNT>
+__device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3 d, float time, int self_ref, float tmin,
+                                            LocalCount<COUNT>& lc) {
+    OwHit h;
+    h.t = RL_INF;
+    h.ref = -1;
+    h.b1 = h.b2 = 0.0f;
+    if (COUNT) lc.rays++;
+    RayPre pre = make_pre(o, d);
+    const float a_dd = dot(d, d);
+    OwHit* hp = &h;
+    LocalCount<COUNT>& lcr = lc;
+    bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, RL_INF, lc, [&](int ref, float tmax) -> float {
+        int type = ref_type(ref), idx = ref_index(ref);
+        if (type == REF_SPHERE) {  // sphere.rs:34-75
+            float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
+            if (COUNT) lcr.prims++;
+            float3 center = fma3(f3(dc), time, f3(c));
+            float3 oc = o - center;
+            float hb = dot(oc, d);
+            float t;
+            if (ref == self_ref) {
+                // origin lies on this sphere: the roots are 0 and -2 hb / a; only the far one is a new hit
+                t = -2.0f * hb / a_dd;
+                if (!(t > 1e-4f * fabsf(c.w) * rsqrtf(a_dd))) return tmax;
+            } else {
+                float tc = -hb / a_dd;
+                float3 perp = fma3(d, tc, oc);
+                float disc = a_dd * (c.w * c.w - dot(perp, perp));
+                if (disc < 0.0f) return tmax;
+                float q = sqrtf(disc) / a_dd;
+                t = tc - q;
+                if (!(t >= tmin && t <= tmax)) {
+                    t = tc + q;
+                    if (!(t >= tmin && t <= tmax)) return tmax;
+                }
+            }
+            if (t < tmax) {
+                hp->t = t;
+                hp->ref = ref;
+                return t;
+            }
+            return tmax;
+        } else if (type == REF_TRI) {  // flat/triangle.rs:60-95 (watertight test instead of the plane basis)
+            if (ref == self_ref) return tmax;
+            float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
+            if (COUNT) lcr.tris++;
+            float t, b1, b2;
+            if (tri_hit(pre, f3(p0), f3(p1), f3(p2), &t, &b1, &b2) && t >= tmin && t < tmax) {
+                hp->t = t;
+                hp->ref = ref;
+                hp->b1 = b1;
+                hp->b2 = b2;
+                return t;
+            }
+            return tmax;
+        } else {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
+            if (ref == self_ref) return tmax;
+            const OwQuad& qd = sc.quads[idx];
+            float4 n4 = qd.n, q4 = qd.q;
+            if (COUNT) lcr.prims++;
+            float denom = dot(f3(n4), d);
+            if (fabsf(denom) < 1e-8f) return tmax;
+            float t = (q4.w - dot(f3(n4), o)) / denom;
+            if (!(t >= tmin && t < tmax)) return tmax;
+            float3 ph = fma3(d, t, o) - f3(q4);
+            float3 w = f3(qd.w);
+            float alpha = dot(w, cross(ph, f3(qd.v)));
+            float beta = dot(w, cross(f3(qd.u), ph));
+            if (!(0.0f <= alpha && alpha <= 1.0f && 0.0f <= beta && beta <= 1.0f)) return tmax;
+            hp->t = t;
+            hp->ref = ref;
+            hp->b1 = alpha;
+            hp->b2 = beta;
+            return t;
+        }
+    });
+    return h;
+}
+
+// state of one path (per lane)
+struct Path {
+    float3 o, d;
+    float3 thr, rad;
+    float time;
+    int depth;
+    int self_ref;
+};
+
+// hit record + material evaluation for one bounce; returns false when the path ends
+template <bool COUNT>
+__device__ __forceinline__ bool ow_bounce(const DevScene& sc, const OwCam& cam, Path& p, uint4 rnd, LocalCount<COUNT>& lc) {
+    float tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f) * rsqrtf(dot(p.d, p.d));
+    OwHit h = ow_closest<COUNT>(sc, p.o, p.d, p.time, p.self_ref, tmin, lc);
+    if (h.ref < 0) {  // camera.rs:256-258
+        p.rad = p.rad + p.thr * cam.background;
+        return false;
+    }
+    if (COUNT) lc.shades++;
+    int type = ref_type(h.ref), idx = ref_index(h.ref);
+    float3 pos, normal;
+    float u = h.b1, v = h.b2;
+    int mat_id;
+    bool uv_from_sphere = false;
+    float3 outward = f3(0.0f, 1.0f, 0.0f);
+    if (type == REF_SPHERE) {
+        float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
+        float3 center = fma3(f3(dc), p.time, f3(c));
+        float3 q = fma3(p.d, h.t, p.o) - center;
+        outward = normalize_precise(q) * (c.w < 0.0f ? -1.0f : 1.0f);  // (p - c) / r keeps the sign of r
+        pos = fma3(normalize_precise(q), fabsf(c.w), center);           // snapped back onto the surface
+        mat_id = __float_as_int(dc.w);
+        uv_from_sphere = true;
+    } else if (type == REF_TRI) {
+        float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
+        float b0 = 1.0f - h.b1 - h.b2;
+        pos = f3(p0) * b0 + f3(p1) * h.b1 + f3(p2) * h.b2;
+        int flags = __float_as_int(p2.w);
+        float4 s0 = sc.tri_shade[idx].s0, s1 = sc.tri_shade[idx].s1, s2 = sc.tri_shade[idx].s2;
+        if (flags & 1) outward = normalize_precise(f3(s1) * h.b1 + f3(s2) * h.b2 + f3(s0) * b0);
+        else outward = f3(s0);
+        if (flags & 2) {
+            float4 s3 = sc.tri_shade[idx].s3;
+            u = s0.w * b0 + s2.w * h.b1 + s3.y * h.b2;
+            v = s1.w * b0 + s3.x * h.b1 + s3.z * h.b2;
+        }
+        mat_id = __float_as_int(p0.w);
+    } else {
+        const OwQuad& qd = sc.quads[idx];
+        outward = f3(qd.n);
+        float3 ip = fma3(p.d, h.t, p.o);
+        pos = ip - outward * (dot(outward, ip) - qd.q.w);  // snapped onto the plane
+        mat_id = __float_as_int(qd.u.w);
+    }
+    bool front = dot(p.d, outward) <= 0.0f;  // hittable/mod.rs:32-38
+    normal = front ? outward : -outward;
+    const DevMaterial m = sc.materials[mat_id];
+    int kind = __float_as_int(m.b.w);
+    int tex = __float_as_int(m.color.w);
+    if (uv_from_sphere && tex >= 0) {  // get_sphere_uv (sphere.rs:91-99); only image textures read it
+        float theta = acosf(fminf(fmaxf(-outward.y, -1.0f), 1.0f));
+        float phi = atan2f(-outward.z, outward.x) + 3.14159265358979f;
+        u = phi * (1.0f / 6.28318530717959f);
+        v = theta * (1.0f / 3.14159265358979f);
+    }
+    if (kind == RL_MAT_OW_DIFFUSE_LIGHT) {  // material.rs:178-195
+        p.rad = p.rad + p.thr * tex_value(sc, tex, u, v, pos);
+        return false;
+    }
+    float3 dir;
+    float3 atten;
+    if (kind == RL_MAT_OW_LAMBERTIAN) {  // material.rs:74-92
+        dir = normal + unit_vector(u01(rnd.x), u01(rnd.y));
+        if (fabsf(dir.x) <= 1e-8f && fabsf(dir.y) <= 1e-8f && fabsf(dir.z) <= 1e-8f) dir = normal;
+        atten = tex_value(sc, tex, u, v, pos);
+    } else if (kind == RL_MAT_OW_METAL) {  // material.rs:105-122
+        float3 refl = p.d - normal * (2.0f * dot(p.d, normal));
+        dir = fma3(unit_vector(u01(rnd.x), u01(rnd.y)), m.a.x, normalize(refl));
+        if (!(dot(dir, normal) > 0.0f)) return false;
+        atten = f3(m.color);
+    } else {  // Dielectric, material.rs:139-176
+        float ri = front ? 1.0f / m.a.y : m.a.y;
+        float3 unit = normalize(p.d);
+        float cos_theta = fminf(-dot(unit, normal), 1.0f);
+        float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+        bool reflect = ri * sin_theta > 1.0f;
+        if (!reflect) {
+            float r0 = (1.0f - ri) / (1.0f + ri);
+            r0 *= r0;
+            float x = 1.0f - cos_theta;
+            float x2 = x * x;
+            reflect = (r0 + (1.0f - r0) * (x2 * x2 * x)) > u01(rnd.z);
+        }
+        if (reflect) {
+            dir = unit - normal * (2.0f * dot(unit, normal));
+        } else {  // vec3.rs:224-230
+            float3 perp = (unit + normal * cos_theta) * ri;
+            float3 par = normal * (-sqrtf(fabsf(1.0f - dot(perp, perp))));
+            dir = perp + par;
+        }
+        atten = f3(1.0f, 1.0f, 1.0f);
+    }
+    p.thr = p.thr * atten;
+    p.o = pos;
+    p.d = dir;
+    p.self_ref = h.ref;
+    p.depth--;
+    return p.depth > 0;  // depth exhausted: the remaining term is black (camera.rs:239-241)
+}
+
+__device__ __forceinline__ void chunk_range(int spp, int n_chunks, int chunk, int* s0, int* s1) {
+    *s0 = (int)(((long long)chunk * spp) / n_chunks);
+    *s1 = (int)(((long long)(chunk + 1) * spp) / n_chunks);
+}
+
+// get_ray (camera.rs:203-230)
+__device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, unsigned sample, Path& p) {
+    uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
+    unsigned pixel = (unsigned)(j * cam.width + i);
+    uint4 r = philox(make_uint4(pixel, sample, 0u, 0u), key);
+    float3 center = cam.pixel00 + cam.du * (float)i + cam.dv * (float)j;
+    float px = -0.5f + u01(r.x), py = -0.5f + u01(r.y);
+    float3 sample_p = center + cam.du * px + cam.dv * py;
+    float3 origin = cam.lookfrom;
+    if (cam.defocus) {
+        // uniform point in the unit disc (polar map; UnitDisc's rejection loop is statistically identical)
+        float rr = sqrtf(u01(r.w));
+        uint4 r2 = philox(make_uint4(pixel, sample, 0u, 1u), key);
+        float s, c;
+        sincospif(2.0f * u01(r2.x), &s, &c);
+        origin = cam.lookfrom + cam.disk_u * (rr * c) + cam.disk_v * (rr * s);
+    }
+    p.o = origin;
+    p.d = sample_p - origin;
+    p.time = u01(r.z);
+    p.thr = f3(1.0f, 1.0f, 1.0f);
+    p.rad = f3(0.0f, 0.0f, 0.0f);
+    p.depth = cam.max_depth;
+    p.self_ref = -1;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_ow_render(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
+                                                   unsigned long long* __restrict__ queue, Counters* counters) {
+    LocalCount<COUNT> lc;
+    const unsigned lane = threadIdx.x & 31;
+    const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
+    // lane state
+    bool has_item = false, alive = false, done = false;
+    int x = 0, y = 0, chunk = 0, s = 0, s_end = 0;
+    float3 acc = f3(0.0f, 0.0f, 0.0f);
+    Path p;
+    p.depth = 0;
+    while (true) {
+        // ---- retire finished items, refill idle lanes (warp-aggregated queue pop) ----
+        if (has_item && !alive && s == s_end) {
+            size_t idx = (((size_t)chunk * cam.height + y) * cam.width + x) * 3;
+            partial[idx + 0] = acc.x;
+            partial[idx + 1] = acc.y;
+            partial[idx + 2] = acc.z;
+            has_item = false;
+        }
+        bool need = !has_item && !done;
+        unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            int leader = __ffs(mask) - 1;
+            unsigned long long base = 0;
+            if (lane == (unsigned)leader) base = atomicAdd(queue, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) {
+                long long item = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
+                // items whose padded pixel falls outside the rectangle are skipped by taking the next round
+                if (item >= jt.n_items) {
+                    done = true;
+                } else {
+                    int j = find_job(jt, item);
+                    rl_job job = jt.jobs[j];
+                    long long local = item - jt.prefix[j];
+                    int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
+                    long long pp = padded_pixels(w, hgt);
+                    int ck = (int)(local / pp);
+                    int px, py;
+                    tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
+                    if (px < w && py < hgt) {
+                        x = job.x0 + px;
+                        y = job.y0 + py;
+                        chunk = job.chunk_begin + ck;
+                        chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                        acc = f3(0.0f, 0.0f, 0.0f);
+                        has_item = true;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, done && !has_item)) break;
+        // ---- path regeneration ----
+        if (has_item && !alive && s < s_end) {
+            ow_camera_ray(cam, x, y, (unsigned)(cam.first_sample + s), p);
+            alive = true;
+        }
+        // ---- one bounce for every live lane ----
+        if (alive) {
+            unsigned pixel = (unsigned)(y * cam.width + x);
+            unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
+            uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
+            bool cont = ow_bounce<COUNT>(sc, cam, p, rnd, lc);
+            if (!cont) {
+                acc = acc + p.rad;  // samples are folded in order (camera.rs:174)
+                alive = false;
+                s++;
+            }
+        }
+    }
+    lc.flush(counters);
+}
+
+// fold the per-chunk partial sums in chunk order
+__global__ void k_ow_reduce(const float* __restrict__ partial, float* __restrict__ out, size_t n, int n_chunks) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.0f;
+    for (int c = 0; c < n_chunks; c++) s += partial[(size_t)c * n + i];
+    out[i] = s;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_ow_trace(DevScene sc, const rl_ray* __restrict__ rays, unsigned long long n,
+                                                  rl_hit* __restrict__ hits, Counters* counters) {
+    LocalCount<COUNT> lc;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        rl_ray r = rays[i];
+        float3 o = f3(r.origin[0], r.origin[1], r.origin[2]), d = f3(r.direction[0], r.direction[1], r.direction[2]);
+        OwHit h = ow_closest<COUNT>(sc, o, d, r.time, -1, 1e-10f, lc);
+        rl_hit out;
+        out.node = -1;
+        out.t = h.t;
+        out.u = h.b1;
+        out.v = h.b2;
+        if (h.ref >= 0) {
+            int type = ref_type(h.ref), idx = ref_index(h.ref);
+            out.node = type == REF_SPHERE ? sc.sphere_node[idx]
+                     : type == REF_QUAD ? sc.quad_node[idx] : __float_as_int(sc.tri_verts[idx].p1.w);
+        }
+        hits[i] = out;
+    }
+    lc.flush(counters);
+}
+
+}  // namespace
+
+int ow_num_chunks(int spp) { return spp <= 0 ? 1 : (spp + 31) / 32; }
+
+int ow_image_height(const rl_ow_camera* c) {
+    double h = (double)c->image_width / c->aspect_ratio;
+    long long hh = h > 0 ? (long long)h : 0;
+    return (int)(hh < 1 ? 1 : hh);
+}
+
+static OwCam make_cam(const rl_ow_camera* p, uint32_t first_sample) {
+    // Camera::new (camera.rs:72-118) in f64 on the host
+    OwCam c{};
+    c.width = p->image_width;
+    c.height = ow_image_height(p);
+    c.spp = p->samples_per_pixel;
+    c.max_depth = p->max_depth;
+    c.first_sample = (int)first_sample;
+    c.n_chunks = ow_num_chunks(p->samples_per_pixel);
+    c.defocus = p->defocus_angle > 0.0 ? 1 : 0;
+    const double PI = 3.14159265358979323846;
+    auto sub = [](const double* a, const double* b, double* o) { for (int k = 0; k < 3; k++) o[k] = a[k] - b[k]; };
+    auto norm = [](double* v) { double m = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int k = 0; k < 3; k++) v[k] /= m; };
+    auto crs = [](const double* a, const double* b, double* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    double theta = p->vfov * PI / 180.0;
+    double h = tan(theta / 2.0);
+    double vh = 2.0 * h * p->focus_dist;
+    double vw = vh * ((double)c.width / (double)c.height);
+    double w[3], u[3], v[3];
+    sub(p->lookfrom, p->lookat, w);
+    norm(w);
+    crs(p->vup, w, u);
+    norm(u);
+    crs(w, u, v);
+    norm(v);
+    double du[3], dv[3], p00[3];
+    for (int k = 0; k < 3; k++) {
+        double vu = vw * u[k], vv = vh * -v[k];
+        du[k] = vu / c.width;
+        dv[k] = vv / c.height;
+        double ul = p->lookfrom[k] - p->focus_dist * w[k] - vu / 2.0 - vv / 2.0;
+        p00[k] = ul + 0.5 * (du[k] + dv[k]);
+    }
+    double dr = p->focus_dist * tan((p->defocus_angle / 2.0) * PI / 180.0);
+    c.lookfrom = make_float3((float)p->lookfrom[0], (float)p->lookfrom[1], (float)p->lookfrom[2]);
+    c.pixel00 = make_float3((float)p00[0], (float)p00[1], (float)p00[2]);
+    c.du = make_float3((float)du[0], (float)du[1], (float)du[2]);
+    c.dv = make_float3((float)dv[0], (float)dv[1], (float)dv[2]);
+    c.disk_u = make_float3((float)(u[0] * dr), (float)(u[1] * dr), (float)(u[2] * dr));
+    c.disk_v = make_float3((float)(v[0] * dr), (float)(v[1] * dr), (float)(v[2] * dr));
+    c.background = make_float3((float)p->background[0], (float)p->background[1], (float)p->background[2]);
+    c.seed_lo = (unsigned)(p->seed & 0xffffffffu);
+    c.seed_hi = (unsigned)(p->seed >> 32);
+    return c;
+}
+
+cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
+                             float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
+                             int sm_count, cudaStream_t stream) {
+    if (jt.n_items <= 0) return cudaSuccess;
+    OwCam c = make_cam(cam, first_sample);
+    cudaError_t e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    if (instrumented) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render<true>, 256, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render<false>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (jt.n_items + 255) / 256;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    if (instrumented) k_ow_render<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters);
+    else k_ow_render<false><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream) {
+    size_t n = (size_t)cam->image_width * ow_image_height(cam) * 3;
+    int nc = ow_num_chunks(cam->samples_per_pixel);
+    k_ow_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_partial, d_out, n, nc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t n, rl_hit* d_hits, Counters* d_counters,
+                            bool instrumented, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (instrumented) k_ow_trace<true><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+    else k_ow_trace<false><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+    return cudaGetLastError();
+}
+
+}  // namespace rl

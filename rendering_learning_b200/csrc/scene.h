@@ -1,0 +1,143 @@
+// Flat (device) scene layout — what the flattener lowers the reference's object tree into.
+// Everything the kernels touch is 16-byte vectors so node / triangle / primitive fetches are single
+// LDG.128 / LDS.128 instructions.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rl_b200.h"
+
+namespace rl {
+
+// primitive kinds on the device
+enum : int {
+    PK_RTC_SPHERE = 1, PK_RTC_PLANE = 2, PK_RTC_CUBE = 3, PK_RTC_CYLINDER = 4, PK_RTC_CONE = 5,
+    PK_TRIANGLE = 8, PK_OW_SPHERE = 9, PK_OW_QUAD = 10
+};
+
+// BVH leaf reference: (type << 28) | index into the per-type array
+constexpr int REF_TRI = 0, REF_SPHERE = 1, REF_QUAD = 2;
+__host__ __device__ inline int make_ref(int type, int index) { return (type << 28) | index; }
+__host__ __device__ inline int ref_type(int ref) { return (ref >> 28) & 7; }
+__host__ __device__ inline int ref_index(int ref) { return ref & 0x0FFFFFFF; }
+
+// RTC analytic primitive (unit shape + composed, pre-inverted transform). 176 B.
+struct RtcPrim {
+    float4 inv[3];   // world -> object affine rows (inv_total = inv_leaf * ... * inv_root)
+    float4 fwd[3];   // object -> world affine rows (maps the surface-snapped local hit point back)
+    float4 pat[3];   // object -> pattern space rows (pattern.inv); identity if no pattern
+    float ymin, ymax;  // cylinder / cone truncation (+-inf when None)
+    int kind, flags;   // flags bit0 = closed
+    int material, node, pad0, pad1;
+};
+
+// triangle: traversal data (48 B) and shading data (64 B) in separate arrays
+struct TriVerts {
+    float4 p0;  // xyz, w = material (int bits)
+    float4 p1;  // xyz, w = source node id (int bits)
+    float4 p2;  // xyz, w = flags (bit0 smooth normals, bit1 has uv) | (xform index + 1) << 8
+};
+struct TriShade {
+    float4 s0;  // n0.xyz, uv0.x      (flat: n0 = the face normal, world space)
+    float4 s1;  // n1.xyz, uv0.y
+    float4 s2;  // n2.xyz, uv1.x
+    float4 s3;  // uv1.y, uv2.x, uv2.y, 0
+};
+struct Xform {  // world -> pattern space for triangles whose material carries a pattern
+    float4 r[3];
+};
+
+struct OwSphere {  // 32 B
+    float4 c;   // centre at time 0, w = radius
+    float4 dc;  // centre(1) - centre(0), w = material (int bits)
+};
+struct OwQuad {  // 80 B
+    float4 q;  // xyz, w = d = n . q
+    float4 u;  // xyz, w = material (int bits)
+    float4 v;  // xyz
+    float4 n;  // unit normal
+    float4 w;  // n_raw / (n_raw . n_raw)
+};
+
+struct DevMaterial {  // 48 B
+    float4 color;  // rgb (RTC surface colour / OW metal albedo), w = texture index (int bits, -1 none)
+    float4 a;      // RTC: ambient, diffuse, specular, shininess | OW: fuzz, refractive_index, 0, 0
+    float4 b;      // RTC: reflectivity, transparency, refractive_index, 0 | w = kind (int bits)
+};
+struct DevTexture {  // 48 B
+    float4 a;  // rgb, w = kind (int bits)
+    float4 b;  // rgb, w = OW checker 1/scale
+    int4 idx;  // OW: tex_a, tex_b, image, 0
+};
+struct DevImage {
+    const float4* texels;  // rgba f32, row-major, top row first
+    int width, height;
+};
+struct DevLight {
+    float4 pos, intensity;
+};
+
+// BVH2 traversal node: both children's boxes live in the parent. 64 B = 4 x LDG.128.
+struct BvhNode {
+    float4 a;  // c0.lo.x c0.lo.y c0.lo.z c0.hi.x
+    float4 b;  // c0.hi.y c0.hi.z c1.lo.x c1.lo.y
+    float4 c;  // c1.lo.z c1.hi.x c1.hi.y c1.hi.z
+    int4 d;    // child0, child1 (>=0 internal node, <0 = ~leaf ref), 0, 0
+};
+
+// everything a kernel needs, passed by value
+struct DevScene {
+    int flavor;
+    int n_prims;      // RTC analytic prims (brute force)
+    int n_tris, n_spheres, n_quads;
+    int n_bvh_prims, n_bvh_nodes;  // traversal nodes (>= 1 when n_bvh_prims >= 1)
+    int n_materials, n_textures, n_lights, n_images, n_xforms;
+    int has_transparency;
+    int max_reflection_depth;
+    float void_color[3];
+    const RtcPrim* prims;
+    const TriVerts* tri_verts;
+    const TriShade* tri_shade;
+    const Xform* xforms;
+    const OwSphere* spheres;
+    const OwQuad* quads;
+    const int* sphere_node;  // source node ids
+    const int* quad_node;
+    const DevMaterial* materials;
+    const DevTexture* textures;
+    const DevImage* images;
+    const DevLight* lights;
+    const BvhNode* nodes;
+};
+
+// host-side result of flattening
+struct FlatScene {
+    int flavor = 0;
+    std::vector<RtcPrim> prims;
+    std::vector<TriVerts> tri_verts;
+    std::vector<TriShade> tri_shade;
+    std::vector<Xform> xforms;
+    std::vector<OwSphere> spheres;
+    std::vector<OwQuad> quads;
+    std::vector<int> sphere_node, quad_node;
+    std::vector<DevMaterial> materials;
+    std::vector<DevTexture> textures;
+    std::vector<DevLight> lights;
+    struct Img { int w, h; std::vector<float4> texels; };
+    std::vector<Img> images;
+    // LBVH input: one AABB + leaf ref + source node per bounded primitive
+    std::vector<float> bvh_aabb;   // [n][6]
+    std::vector<int> bvh_ref;      // [n]
+    std::vector<int> bvh_node_id;  // [n]
+    int has_transparency = 0;
+    int max_reflection_depth = 5;
+    float void_color[3] = {0, 0, 0};
+};
+
+// returns RL_OK or an RL_E_* code and fills `err`
+int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err);
+
+}  // namespace rl

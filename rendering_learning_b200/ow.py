@@ -264,34 +264,47 @@ class Triangle(Hittable):
                            param=sd.add_params(vals))
 
 
+class _ctor_or_builder:
+    """`Transform::rotate_y(object, deg)` on the class, `hittable.rotate_y(deg)` on an instance
+    (the reference has both: transform.rs:22-86 and the builder methods of hittable/mod.rs:56-85)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __get__(self, inst, owner):
+        if inst is None:
+            return lambda obj, arg: self.fn(owner, obj, arg)
+        return lambda arg: self.fn(owner, inst, arg)
+
+
 class Transform(Hittable):
     """hittable/transform.rs:21-86 — forward and inverse 3x3 are both written out by the ctor."""
 
     def __init__(self, obj: Hittable, m, minv):
         self.object, self.m, self.minv = obj, m, minv
 
-    @classmethod
+    @_ctor_or_builder
     def rotate_x(cls, obj, degrees):
         r = math.radians(degrees)
         s, c = math.sin(r), math.cos(r)
         return cls(obj, [[1.0, 0.0, 0.0], [0.0, c, -s], [0.0, s, c]],
                    [[1.0, 0.0, 0.0], [0.0, c, s], [0.0, -s, c]])
 
-    @classmethod
+    @_ctor_or_builder
     def rotate_y(cls, obj, degrees):
         r = math.radians(degrees)
         s, c = math.sin(r), math.cos(r)
         return cls(obj, [[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]],
                    [[c, 0.0, -s], [0.0, 1.0, 0.0], [s, 0.0, c]])
 
-    @classmethod
+    @_ctor_or_builder
     def rotate_z(cls, obj, degrees):
         r = math.radians(degrees)
         s, c = math.sin(r), math.cos(r)
         return cls(obj, [[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]],
                    [[c, s, 0.0], [-s, c, 0.0], [0.0, 0.0, 1.0]])
 
-    @classmethod
+    @_ctor_or_builder
     def scale(cls, obj, scale):
         s = float(scale)
         i = 1.0 / s

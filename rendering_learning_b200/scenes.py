@@ -205,3 +205,141 @@ def ow_test_scene():
                              defocus_angle=10.0, focus_dist=3.4,
                              background=ow.Color(0.7, 0.8, 1.0), seed=0)
     return world, params
+
+
+class _Xoshiro256PlusPlus:
+    """rand_xoshiro 0.6.0 `Xoshiro256PlusPlus::seed_from_u64` (SplitMix64 seeding) + rand 0.8.5 float
+    sampling.  Used only to lay out the cover scene like OW/examples/bouncing_spheres.rs:16; the crate
+    source is not vendored, so the exact layout is "parity unpinned"  — the oracle and the
+    GPU consume the SAME generated spheres, which is all the parity tests need."""
+    M = (1 << 64) - 1
+
+    def __init__(self, seed: int):
+        s = seed & self.M
+        st = []
+        for _ in range(4):
+            s = (s + 0x9E3779B97F4A7C15) & self.M
+            z = s
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & self.M
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & self.M
+            st.append(z ^ (z >> 31))
+        self.s = st
+
+    @staticmethod
+    def _rotl(x, k):
+        return ((x << k) | (x >> (64 - k))) & _Xoshiro256PlusPlus.M
+
+    def next_u64(self) -> int:
+        s = self.s
+        r = (self._rotl((s[0] + s[3]) & self.M, 23) + s[0]) & self.M
+        t = (s[1] << 17) & self.M
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = self._rotl(s[3], 45)
+        return r
+
+    def gen(self) -> float:
+        return (self.next_u64() >> 11) * (1.0 / 9007199254740992.0)
+
+    def gen_range(self, low: float, high: float) -> float:
+        import struct
+        scale = high - low
+        while True:
+            bits = (self.next_u64() >> 12) | 0x3FF0000000000000
+            v12 = struct.unpack("<d", struct.pack("<Q", bits))[0]
+            res = v12 * scale + (low - scale)
+            if res < high:
+                return res
+
+
+def ow_cover_world():
+    """OW/examples/bouncing_spheres.rs:16-117 — the RTIOW cover scene (BASELINE config C4)."""
+    from . import ow
+    rng = _Xoshiro256PlusPlus(1)
+    world = []
+    checker = ow.Checker.new(0.32, ow.SolidColor(ow.Color(0.2, 0.23, 0.1)), ow.SolidColor(ow.Color(0.9, 0.9, 0.9)))
+    world.append(ow.Sphere(ow.Center.Stationary(ow.Point3(0.0, -1000.0, 0.0)), 1000.0, ow.Lambertian(checker)))
+    for a in range(-11, 11):
+        for b in range(-11, 11):
+            choose_mat = rng.gen()
+            cx = a + 0.9 * rng.gen()
+            cz = b + 0.9 * rng.gen()
+            center = ow.Point3(cx, 0.2, cz)
+            dx, dy, dz = cx - 4.0, 0.2 - 0.2, cz - 0.0
+            if math.sqrt(dx * dx + dy * dy + dz * dz) > 0.9:
+                if choose_mat < 0.8:
+                    c2 = ow.Point3(cx + 0.0, 0.2 + rng.gen_range(0.0, 0.5), cz + 0.0)
+                    c_a = (rng.gen(), rng.gen(), rng.gen())
+                    c_b = (rng.gen(), rng.gen(), rng.gen())
+                    albedo = ow.Color(c_a[0] * c_b[0], c_a[1] * c_b[1], c_a[2] * c_b[2])
+                    world.append(ow.Sphere(ow.Center.Moving(center, c2), 0.2, ow.Lambertian(ow.SolidColor(albedo))))
+                elif choose_mat < 0.95:
+                    albedo = ow.Color(rng.gen_range(0.5, 1.0), rng.gen_range(0.5, 1.0), rng.gen_range(0.5, 1.0))
+                    fuzz = rng.gen()
+                    world.append(ow.Sphere(ow.Center.Stationary(center), 0.2, ow.Metal(albedo, fuzz)))
+                else:
+                    world.append(ow.Sphere(ow.Center.Stationary(center), 0.2, ow.Dielectric(1.5)))
+    world.append(ow.Sphere(ow.Center.Stationary(ow.Point3(0.0, 1.0, 0.0)), 1.0, ow.Dielectric(1.5)))
+    world.append(ow.Sphere(ow.Center.Stationary(ow.Point3(-4.0, 1.0, 0.0)), 1.0,
+                           ow.Lambertian(ow.SolidColor(ow.Color(0.4, 0.2, 0.1)))))
+    world.append(ow.Sphere(ow.Center.Stationary(ow.Point3(4.0, 1.0, 0.0)), 1.0, ow.Metal(ow.Color(0.7, 0.6, 0.5), 0.0)))
+    return ow.Bvh.new(world)
+
+
+def ow_cover_params(image_width=1200, samples_per_pixel=500, max_depth=50, seed=0):
+    """bouncing_spheres.rs:121-131 camera at the BASELINE C4 size (1200x675, 500 spp, depth 50)."""
+    from . import ow
+    return ow.CameraParams(aspect_ratio=16.0 / 9.0, image_width=image_width,
+                           samples_per_pixel=samples_per_pixel, max_depth=max_depth, vfov=20.0,
+                           lookfrom=ow.Point3(13.0, 2.0, 3.0), lookat=ow.Point3(0.0, 0.0, 0.0),
+                           vup=ow.Vec3(0.0, 1.0, 0.0), defocus_angle=0.6, focus_dist=10.0, seed=seed)
+
+
+def ow_spot_texture() -> np.ndarray:
+    """cow.rs:19-30: decode -> into_rgb32f (u8/255 as f32) -> srgb_to_linear in f64 -> f32."""
+    from . import ow
+    rgb8 = np.load(os.path.join(ASSETS, "spot_texture.npz"))["rgb8"]
+    f = (rgb8.astype(np.float32) / np.float32(255.0)).astype(np.float64)
+    return ow.srgb.srgb_to_linear(f).astype(np.float32)
+
+
+def ow_cow_world():
+    """OW/examples/cow.rs:17-117 — Cornell box + textured spot (BASELINE config C5)."""
+    from . import ow
+    m = load_mesh("spot")
+    cow_surface = ow.Lambertian(ow.Image(ow_spot_texture()))
+    tris = []
+    P, UV, N = m["tri_p"], m["tri_uv"], m["tri_n"]
+    for i in range(P.shape[0]):
+        pts = [tuple(P[i, k]) for k in range(3)]
+        uv = [tuple(UV[i, k]) for k in range(3)] if m["has_uv"][i] else None
+        ns = [tuple(N[i, k]) for k in range(3)] if m["has_n"][i] else None
+        tris.append(ow.Triangle.from_model(pts, uv, ns, cow_surface))
+    cow = ow.Bvh.new(tris).scale(200.0).rotate_y(45.0).translate(ow.Vec3(240.0, 165.0, 240.0))
+    red = ow.Lambertian(ow.SolidColor(ow.Color(0.65, 0.05, 0.05)))
+    white = ow.Lambertian(ow.SolidColor(ow.Color(0.73, 0.73, 0.73)))
+    green = ow.Lambertian(ow.SolidColor(ow.Color(0.12, 0.45, 0.15)))
+    light = ow.DiffuseLight(ow.SolidColor(ow.Color(5.0, 5.0, 5.0)))
+    world = [
+        ow.Quad.new(ow.Point3(555.0, 0.0, 0.0), ow.Vec3(0.0, 555.0, 0.0), ow.Vec3(0.0, 0.0, 555.0), green),
+        ow.Quad.new(ow.Point3(0.0, 0.0, 0.0), ow.Vec3(0.0, 555.0, 0.0), ow.Vec3(0.0, 0.0, 555.0), red),
+        ow.Quad.new(ow.Point3(113.0, 554.0, 127.0), ow.Vec3(330.0, 0.0, 0.0), ow.Vec3(0.0, 0.0, 305.0), light),
+        ow.Quad.new(ow.Point3(0.0, 0.0, 0.0), ow.Vec3(555.0, 0.0, 0.0), ow.Vec3(0.0, 0.0, 555.0), white),
+        ow.Quad.new(ow.Point3(555.0, 555.0, 555.0), ow.Vec3(-555.0, 0.0, 0.0), ow.Vec3(0.0, 0.0, -555.0), white),
+        ow.Quad.new(ow.Point3(0.0, 0.0, 555.0), ow.Vec3(555.0, 0.0, 0.0), ow.Vec3(0.0, 555.0, 0.0), white),
+        cow,
+    ]
+    return ow.Bvh.new(world)
+
+
+def ow_cow_params(image_width=3840, samples_per_pixel=256, max_depth=40, seed=0, aspect_ratio=16.0 / 9.0):
+    """cow.rs:121-136 camera at the BASELINE C5 size (3840x2160, 256 spp, depth 40)."""
+    from . import ow
+    return ow.CameraParams(aspect_ratio=aspect_ratio, image_width=image_width,
+                           samples_per_pixel=samples_per_pixel, max_depth=max_depth,
+                           background=ow.Color(0.0, 0.0, 0.0), vfov=40.0,
+                           lookfrom=ow.Point3(278.0, 278.0, -800.0), lookat=ow.Point3(278.0, 278.0, 0.0),
+                           vup=ow.Vec3(0.0, 1.0, 0.0), defocus_angle=0.0, seed=seed)
