@@ -241,5 +241,5 @@ def test_camera_rays_and_render(oracle):  # camera.rs:176-273
     img = oracle.rtc_render(world(basic_spheres()), cam3.abi(), 1)
     assert np.allclose(img[5, 5], (0.38066, 0.47583, 0.2855), atol=1e-5)
     # AA sub-sample order: nx-major (camera.rs:227-254)
-    r2 = oracle.rtc_camera_rays(rtc.Camera.new(2, 2, math.pi / 2).abi(), 2).reshape(2, 2, 4, 6)
+    r2 = oracle.rtc_camera_rays(rtc.Camera.default(2, 2, math.pi / 2).abi(), 2).reshape(2, 2, 4, 6)
     assert r2[0, 0, 0, 3] > r2[0, 0, 2, 3] and r2[0, 0, 0, 4] > r2[0, 0, 1, 4]
