@@ -229,6 +229,9 @@ void rl_destroy(rl_ctx* ctx);
 const char* rl_last_error(const rl_ctx* ctx); /* ctx may be NULL: error of the last failed rl_create */
 int rl_abi_version(void);
 int rl_device_info(rl_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+/* block until everything queued on the ctx's own stream has finished (the `*_device` entry points that
+ * are given stream = 0 run there) */
+int rl_synchronize(rl_ctx* ctx);
 
 /* ---- scene -------------------------------------------------------------------------------------- */
 /* Replaces walking `World.objects` (RTC/src/scene/world.rs:46-55) / `world.hit` (OW/src/camera.rs:247):

@@ -43,6 +43,9 @@ class Context:
                                             C.byref(hb)))
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hb.value}
 
+    def synchronize(self):
+        self._check(self.lib.rl_synchronize(self.h))
+
     def scene_upload(self, desc: SceneDesc):
         d = desc.freeze()
         self._check(self.lib.rl_scene_upload(self.h, C.byref(d)))

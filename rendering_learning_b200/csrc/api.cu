@@ -164,6 +164,13 @@ int rl_device_info(rl_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int64
     return RL_OK;
 }
 
+int rl_synchronize(rl_ctx* c) {
+    if (!c) return RL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RL_OK;
+}
+
 int rl_set_instrumented(rl_ctx* c, int enabled) {
     if (!c) return RL_E_INVALID;
     c->instrumented = enabled != 0;

@@ -19,6 +19,8 @@
 namespace rl {
 namespace {
 
+constexpr float OW_BIG_RADIUS = 64.0f;  // spheres at least this large take the f64 quadratic
+
 struct OwCam {
     int width, height, spp, max_depth;
     int first_sample, n_chunks, defocus, pad;
@@ -104,6 +106,23 @@ __device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3
                 // origin lies on this sphere: the roots are 0 and -2 hb / a; only the far one is a new hit
                 t = -2.0f * hb / a_dd;
                 if (!(t > 1e-4f * fabsf(c.w) * rsqrtf(a_dd))) return tmax;
+            } else if (fabsf(c.w) >= OW_BIG_RADIUS) {
+                // a huge sphere seen from near its surface (the r = 1000 ground of the cover scene): r^2 - |perp|^2
+                // cancels ~7 digits, more than f32 has.  One such primitive sits near the BVH root, so its
+                // quadratic is evaluated in f64 (B200 runs FP64 at half the FP32 rate; the cost is one test per ray).
+                double ox = (double)oc.x, oy = (double)oc.y, oz = (double)oc.z;
+                double dx = (double)d.x, dy = (double)d.y, dz = (double)d.z;
+                double a = dx * dx + dy * dy + dz * dz;
+                double hbd = ox * dx + oy * dy + oz * dz;
+                double cc = ox * ox + oy * oy + oz * oz - (double)c.w * (double)c.w;
+                double disc = hbd * hbd - a * cc;
+                if (disc < 0.0) return tmax;
+                double sq = sqrt(disc);
+                t = (float)((-hbd - sq) / a);
+                if (!(t >= tmin && t <= tmax)) {
+                    t = (float)((-hbd + sq) / a);
+                    if (!(t >= tmin && t <= tmax)) return tmax;
+                }
             } else {
                 float tc = -hb / a_dd;
                 float3 perp = fma3(d, tc, oc);
@@ -356,8 +375,12 @@ __global__ void __launch_bounds__(256) k_ow_render(DevScene sc, OwCam cam, JobTa
         if (__all_sync(0xffffffffu, done && !has_item)) break;
         // ---- path regeneration ----
         if (has_item && !alive && s < s_end) {
-            ow_camera_ray(cam, x, y, (unsigned)(cam.first_sample + s), p);
-            alive = true;
+            if (cam.max_depth <= 0) {
+                s = s_end;  // depth 0: every sample is black (camera.rs:239-241)
+            } else {
+                ow_camera_ray(cam, x, y, (unsigned)(cam.first_sample + s), p);
+                alive = true;
+            }
         }
         // ---- one bounce for every live lane ----
         if (alive) {
