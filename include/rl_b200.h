@@ -233,6 +233,10 @@ int rl_device_info(rl_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int
  * are given stream = 0 run there) */
 int rl_synchronize(rl_ctx* ctx);
 
+/* Roofline denominators of this path, measured on the ctx's device: non-tensor FP32 FMA throughput
+ * (TFLOP/s), L2-resident read bandwidth and HBM read bandwidth (GB/s).  Takes a few milliseconds. */
+int rl_measure_peaks(rl_ctx* ctx, double* fp32_tflops, double* l2_gbs, double* hbm_gbs);
+
 /* ---- scene -------------------------------------------------------------------------------------- */
 /* Replaces walking `World.objects` (RTC/src/scene/world.rs:46-55) / `world.hit` (OW/src/camera.rs:247):
  * flattens the tree, uploads SoA buffers and builds the LBVH on the device. */
@@ -265,7 +269,9 @@ int rl_ow_num_chunks(const rl_ow_camera* cam);
  *   RTC: d_out_rgb [H][W][3] f32, pixels outside the jobs are left untouched.
  *   OW : d_partial [n_chunks][H][W][3] f32 per-chunk partial sums (untouched outside the jobs);
  *        rl_ow_reduce_device folds the chunks in order into d_out_rgb_sum [H][W][3].
- * `stream` is a cudaStream_t (0 = default stream). */
+ * `stream` is a cudaStream_t; 0 = the ctx's own non-blocking stream (pass cudaStreamLegacy, 0x1, for the
+ * legacy default stream).  With stats == NULL the call only LAUNCHES (asynchronous); errors and overflows
+ * then surface at rl_synchronize. */
 int rl_render_rtc_device(rl_ctx* ctx, const rl_rtc_camera* cam, uint32_t anti_aliasing_samples,
                          const rl_job* jobs, int32_t n_jobs, void* d_out_rgb, void* stream,
                          rl_stats* stats);

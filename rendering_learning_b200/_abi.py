@@ -164,6 +164,7 @@ SYMBOLS = {
     "rl_device_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int64)]),
     "rl_synchronize": (C.c_int, [_P]),
+    "rl_measure_peaks": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rl_scene_upload": (C.c_int, [_P, C.POINTER(rl_scene_desc)]),
     "rl_scene_info_get": (C.c_int, [_P, C.POINTER(rl_scene_info)]),
     "rl_lbvh_download": (C.c_int, [_P, C.POINTER(rl_lbvh_host)]),

@@ -46,6 +46,11 @@ class Context:
     def synchronize(self):
         self._check(self.lib.rl_synchronize(self.h))
 
+    def measure_peaks(self) -> dict:
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.rl_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"fp32_tflops": a.value, "l2_gbs": b.value, "hbm_gbs": c.value}
+
     def scene_upload(self, desc: SceneDesc):
         d = desc.freeze()
         self._check(self.lib.rl_scene_upload(self.h, C.byref(d)))
@@ -141,20 +146,21 @@ class Context:
             arr[i] = A.rl_job(*j)
         return arr
 
-    def render_rtc_device(self, cam, aa_samples, jobs, d_out_ptr: int, stream: int = 0):
-        stats = A.rl_stats()
+    def render_rtc_device(self, cam, aa_samples, jobs, d_out_ptr: int, stream: int = 0, sync: bool = True):
+        """sync=False launches and returns (no stats); call synchronize() to wait and surface errors."""
+        stats = A.rl_stats() if sync else None
         arr = self._jobs(jobs)
         self._check(self.lib.rl_render_rtc_device(self.h, C.byref(cam), C.c_uint32(aa_samples), arr,
-                                                  len(jobs), C.c_void_p(d_out_ptr),
-                                                  C.c_void_p(stream), C.byref(stats)))
+                                                  len(jobs), C.c_void_p(d_out_ptr), C.c_void_p(stream),
+                                                  C.byref(stats) if sync else None))
         return stats
 
-    def render_ow_device(self, cam, first_sample, jobs, d_partial_ptr: int, stream: int = 0):
-        stats = A.rl_stats()
+    def render_ow_device(self, cam, first_sample, jobs, d_partial_ptr: int, stream: int = 0, sync: bool = True):
+        stats = A.rl_stats() if sync else None
         arr = self._jobs(jobs)
         self._check(self.lib.rl_render_ow_device(self.h, C.byref(cam), C.c_uint32(first_sample), arr,
-                                                 len(jobs), C.c_void_p(d_partial_ptr),
-                                                 C.c_void_p(stream), C.byref(stats)))
+                                                 len(jobs), C.c_void_p(d_partial_ptr), C.c_void_p(stream),
+                                                 C.byref(stats) if sync else None))
         return stats
 
     def ow_reduce_device(self, cam, d_partial_ptr: int, d_out_ptr: int, stream: int = 0):

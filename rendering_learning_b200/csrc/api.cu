@@ -13,6 +13,7 @@
 
 namespace rl {
 bool invert_affine_4x4(const double* m16, double* inv12, std::string* err);
+cudaError_t measure_peaks(cudaStream_t s, int sm_count, double* fp32_tflops, double* l2_gbs, double* hbm_gbs);
 }
 
 using namespace rl;
@@ -134,6 +135,7 @@ int rl_create(int device_id, rl_ctx** out) {
         delete c;
         return RL_E_CUDA;
     }
+    cudaMemset(c->counters.p, 0, sizeof(Counters));
     *out = c;
     return RL_OK;
 }
@@ -168,6 +170,21 @@ int rl_synchronize(rl_ctx* c) {
     if (!c) return RL_E_INVALID;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaDeviceSynchronize());  // asynchronous launches may have gone to a caller-provided stream
+    Counters h;
+    CK(c, cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.overflow) {
+        cudaMemset(c->counters.p, 0, sizeof(Counters));
+        c->error = "a traversal stack / work list overflowed on the device";
+        return RL_E_OVERFLOW;
+    }
+    return RL_OK;
+}
+
+int rl_measure_peaks(rl_ctx* c, double* fp32_tflops, double* l2_gbs, double* hbm_gbs) {
+    if (!c) return RL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, measure_peaks(c->stream, c->sm_count, fp32_tflops, l2_gbs, hbm_gbs));
     return RL_OK;
 }
 
@@ -357,15 +374,26 @@ static int make_job_table(rl_ctx* c, const rl_job* jobs, int n_jobs, int width, 
         }
         prefix[i + 1] = prefix[i] + items;
     }
-    CK(c, c->jobs.reserve(sizeof(rl_job) * (size_t)(n_jobs > 0 ? n_jobs : 1)));
+    jt->n_jobs = n_jobs;
+    jt->n_items = prefix[n_jobs];
+    jt->jobs = nullptr;
+    jt->prefix = nullptr;
+    if (n_jobs <= JOBS_INLINE) {
+        // small tables ride in the kernel parameters: nothing to upload, safe for back-to-back async launches
+        jt->inline_jobs = 1;
+        for (int i = 0; i < n_jobs; i++) jt->ijobs[i] = jobs[i];
+        for (int i = 0; i <= n_jobs; i++) jt->iprefix[i] = prefix[i];
+        return RL_OK;
+    }
+    jt->inline_jobs = 0;
+    CK(c, c->jobs.reserve(sizeof(rl_job) * (size_t)n_jobs));
     CK(c, c->prefix.reserve(sizeof(long long) * (size_t)(n_jobs + 1)));
-    if (n_jobs > 0) CK(c, cudaMemcpyAsync(c->jobs.p, jobs, sizeof(rl_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, s));
+    CK(c, cudaStreamSynchronize(s));  // a previous launch on this stream may still read the old table
+    CK(c, cudaMemcpyAsync(c->jobs.p, jobs, sizeof(rl_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, s));
     CK(c, cudaMemcpyAsync(c->prefix.p, prefix.data(), sizeof(long long) * (size_t)(n_jobs + 1), cudaMemcpyHostToDevice, s));
     CK(c, cudaStreamSynchronize(s));  // `prefix` is a local
     jt->jobs = c->jobs.as<rl_job>();
     jt->prefix = c->prefix.as<long long>();
-    jt->n_jobs = n_jobs;
-    jt->n_items = prefix[n_jobs];
     return RL_OK;
 }
 
@@ -419,6 +447,11 @@ int rl_render_rtc_device(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, const
     JobTable jt;
     int rc = make_job_table(c, jobs, n_jobs, cam->hsize, cam->vsize, 1, false, s, &jt);
     if (rc != RL_OK) return rc;
+    if (!stats) {
+        // asynchronous mode: launch and return; overflow stays sticky in the counters until rl_synchronize
+        CK(c, launch_rtc_render(c->ds, cam, inv, aa, jt, (float*)d_out_rgb, c->counters.as<Counters>(), false, s));
+        return RL_OK;
+    }
     CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
     CK(c, cudaEventRecord(c->ev0, s));
     CK(c, launch_rtc_render(c->ds, cam, inv, aa, jt, (float*)d_out_rgb, c->counters.as<Counters>(), c->instrumented, s));
@@ -433,7 +466,7 @@ int rl_render_rtc_device(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, const
     long long px = 0;
     for (int i = 0; i < n_jobs; i++) px += (long long)(jobs[i].x1 - jobs[i].x0) * (jobs[i].y1 - jobs[i].y0);
     st.samples = (uint64_t)px * aa * aa;
-    if (stats) *stats = st;
+    *stats = st;
     return rc;
 }
 
@@ -444,7 +477,9 @@ int rl_render_rtc(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, float* out_r
     CK(c, cudaSetDevice(c->device));
     CK(c, c->frame.reserve(bytes));
     rl_job job{0, 0, cam->hsize, cam->vsize, 0, 1};
-    int rc = rl_render_rtc_device(c, cam, aa, &job, 1, c->frame.p, nullptr, stats);
+    rl_stats st{};
+    int rc = rl_render_rtc_device(c, cam, aa, &job, 1, c->frame.p, nullptr, &st);
+    if (stats) *stats = st;
     if (rc != RL_OK) return rc;
     CK(c, cudaMemcpyAsync(out_rgb, c->frame.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -469,6 +504,12 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
     JobTable jt;
     int rc = make_job_table(c, jobs, n_jobs, cam->image_width, H, nc, true, s, &jt);
     if (rc != RL_OK) return rc;
+    if (!stats) {
+        // asynchronous mode (multi-GPU tile loop): launch and return; errors surface at rl_synchronize
+        CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
+                               c->counters.as<Counters>(), false, c->sm_count, s));
+        return RL_OK;
+    }
     CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
     CK(c, cudaEventRecord(c->ev0, s));
     CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
@@ -490,7 +531,7 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
         }
     }
     st.samples = samples;
-    if (stats) *stats = st;
+    *stats = st;
     return rc;
 }
 

@@ -218,18 +218,26 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
 // ---- work distribution ----------------------------------------------------------------------------------
 // jobs = pixel rectangles (x sample-chunk ranges for OW); item enumeration walks 8x4 pixel micro-tiles so
 // that the 32 lanes of a warp start on neighbouring pixels.
+constexpr int JOBS_INLINE = 8;
 struct JobTable {
-    const rl_job* jobs;      // device copy
+    const rl_job* jobs;      // device copy (used when n_jobs > JOBS_INLINE)
     const long long* prefix; // [n_jobs + 1] exclusive prefix of item counts
     int n_jobs;
+    int inline_jobs;         // 1: the table travels in the kernel parameters (no device buffer, async-safe)
     long long n_items;
+    rl_job ijobs[JOBS_INLINE];
+    long long iprefix[JOBS_INLINE + 1];
 };
+__device__ __forceinline__ long long jt_prefix(const JobTable& jt, int j) {
+    return jt.inline_jobs ? jt.iprefix[j] : jt.prefix[j];
+}
+__device__ __forceinline__ rl_job jt_job(const JobTable& jt, int j) { return jt.inline_jobs ? jt.ijobs[j] : jt.jobs[j]; }
 
 __device__ __forceinline__ int find_job(const JobTable& jt, long long item) {
     int lo = 0, hi = jt.n_jobs - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
-        if (jt.prefix[mid] <= item) lo = mid; else hi = mid - 1;
+        if (jt_prefix(jt, mid) <= item) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -237,14 +245,12 @@ __device__ __forceinline__ int find_job(const JobTable& jt, long long item) {
 // pixel index within a w x h rectangle, enumerated in 8x4 micro-tiles (row-major tiles, row-major inside)
 __device__ __forceinline__ void tile_pixel(int w, int h, long long p, int* x, int* y) {
     int tiles_x = (w + 7) >> 3;
-    long long full_rows = (long long)(h >> 2);             // complete 4-row bands
     long long band_px = (long long)tiles_x * 32;           // padded pixels per band
     long long band = p / band_px;
     int in_band = (int)(p - band * band_px);
     int tile = in_band >> 5, lane = in_band & 31;
     *x = tile * 8 + (lane & 7);
     *y = (int)band * 4 + (lane >> 3);
-    (void)full_rows;
 }
 __host__ __device__ __forceinline__ long long padded_pixels(int w, int h) {
     return (long long)((w + 7) >> 3) * 32 * (long long)((h + 3) >> 2);

@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(256) k_ow_render(DevScene sc, OwCam cam, JobTa
                     done = true;
                 } else {
                     int j = find_job(jt, item);
-                    rl_job job = jt.jobs[j];
-                    long long local = item - jt.prefix[j];
+                    rl_job job = jt_job(jt, j);
+                    long long local = item - jt_prefix(jt, j);
                     int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
                     long long pp = padded_pixels(w, hgt);
                     int ck = (int)(local / pp);

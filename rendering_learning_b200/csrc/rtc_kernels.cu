@@ -635,9 +635,9 @@ __global__ void __launch_bounds__(128) k_rtc_render(DevScene sc, RtcCam cam, Job
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (item < jt.n_items) {
         int j = find_job(jt, item);
-        rl_job job = jt.jobs[j];
+        rl_job job = jt_job(jt, j);
         int x, y;
-        tile_pixel(job.x1 - job.x0, job.y1 - job.y0, item - jt.prefix[j], &x, &y);
+        tile_pixel(job.x1 - job.x0, job.y1 - job.y0, item - jt_prefix(jt, j), &x, &y);
         x += job.x0;
         y += job.y0;
         if (x < job.x1 && y < job.y1) {

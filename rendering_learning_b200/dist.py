@@ -1,0 +1,131 @@
+"""Multi-GPU sharding of the per-pixel ray loop: one process per GPU, a dynamic tile queue, and a
+framebuffer gather over NVLink with NCCL (torch.distributed is the plumbing).
+
+The path shards naturally (pixels and samples are independent): the scene + LBVH are
+replicated on every GPU (<= 5 MB), the image is cut into jobs = pixel rectangles x sample-chunk ranges, and
+ranks pull jobs from ONE shared counter (an atomic fetch-add served by the c10d store, so it works across
+processes) because per-tile cost varies > 10x (sky vs glass).  There is no data-path collective during
+rendering; the only exchange is the final gather: every (chunk, pixel) slot is written by exactly one
+rank and is zero elsewhere, so a SUM reduce to rank 0 is exact (x + 0 == x) and the folded image is
+bit-identical for any GPU count and any schedule.
+
+`launch` callables keep this module testable on CPU with the gloo backend (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+Job = tuple  # (x0, y0, x1, y1, chunk_begin, chunk_end)
+
+
+def make_jobs(width: int, height: int, n_chunks: int, rows_per_job: int, chunks_per_job: int = 1) -> list[Job]:
+    """Row bands x chunk groups, chunk-major so neighbouring jobs touch neighbouring memory."""
+    rows_per_job = max(4, (rows_per_job + 3) // 4 * 4)  # keep the 8x4 micro-tiles whole
+    jobs = []
+    for c0 in range(0, n_chunks, chunks_per_job):
+        for y0 in range(0, height, rows_per_job):
+            jobs.append((0, y0, width, min(y0 + rows_per_job, height), c0, min(c0 + chunks_per_job, n_chunks)))
+    return jobs
+
+
+def jobs_for(width: int, height: int, n_chunks: int, world_size: int, jobs_per_rank: int = 16) -> list[Job]:
+    """About `jobs_per_rank` jobs per GPU: fine enough to balance, coarse enough to amortise a launch."""
+    want = max(1, world_size * jobs_per_rank)
+    bands = max(1, -(-want // n_chunks))
+    rows = max(4, -(-height // bands))
+    return make_jobs(width, height, n_chunks, rows)
+
+
+class TileQueue:
+    """Dynamic job queue: `pop` is an atomic fetch-add on a counter every rank shares."""
+
+    def __init__(self, store, key: str, n_jobs: int):
+        self.store, self.key, self.n_jobs = store, key, n_jobs
+
+    def pop(self):
+        v = self.store.add(self.key, 1) - 1
+        return v if v < self.n_jobs else None
+
+
+class StaticQueue:
+    """Round-robin assignment (used for the millisecond-scale RTC configs)."""
+
+    def __init__(self, rank: int, world_size: int, n_jobs: int):
+        self.it = iter(range(rank, n_jobs, world_size))
+
+    def pop(self):
+        return next(self.it, None)
+
+
+def drain(queue, launch: Callable[[int], None]) -> list[int]:
+    """Pull jobs until the queue is empty; `launch(j)` must be asynchronous so the next pop overlaps it."""
+    mine = []
+    while True:
+        j = queue.pop()
+        if j is None:
+            return mine
+        launch(j)
+        mine.append(j)
+
+
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def current_stream_handle() -> int:
+    """cudaStream_t of torch's current stream.  The C ABI reads 0 as "the ctx's own stream", so the legacy
+    default stream is passed as cudaStreamLegacy (0x1) to keep the launch on the stream torch events see."""
+    import torch
+    h = torch.cuda.current_stream().cuda_stream
+    return h if h else 1
+
+
+def default_store():
+    import torch.distributed as dist
+    return dist.distributed_c10d._get_default_store()
+
+
+def render_ow_distributed(ctx, cam, first_sample: int, jobs: Sequence[Job], partial, out, step_key: str,
+                          store=None, static: bool = False):
+    """One OW render sharded over the ranks of the default process group.
+
+    partial: [n_chunks, H, W, 3] f32 device tensor on every rank; out: [H, W, 3] f32 (written on rank 0).
+    Returns the job ids this rank rendered."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = _rank_world()
+    stream = current_stream_handle()
+    partial.zero_()
+    if static or world == 1:
+        q = StaticQueue(rank, world, len(jobs))
+    else:
+        q = TileQueue(store or default_store(), f"rl_q_{step_key}", len(jobs))
+    mine = drain(q, lambda j: ctx.render_ow_device(cam, first_sample, [jobs[j]], partial.data_ptr(), stream, sync=False))
+    if world > 1:
+        dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM)  # NCCL over NVLink; zeros elsewhere => exact
+    if rank == 0:
+        ctx.ow_reduce_device(cam, partial.data_ptr(), out.data_ptr(), stream)
+    return mine
+
+
+def render_rtc_distributed(ctx, cam, aa: int, jobs: Sequence[Job], frame, step_key: str, store=None,
+                           static: bool = True):
+    """One RTC render sharded over the ranks; frame: [H, W, 3] f32 device tensor (complete on rank 0)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = _rank_world()
+    stream = current_stream_handle()
+    frame.zero_()
+    if static or world == 1:
+        q = StaticQueue(rank, world, len(jobs))
+    else:
+        q = TileQueue(store or default_store(), f"rl_q_{step_key}", len(jobs))
+    mine = drain(q, lambda j: ctx.render_rtc_device(cam, aa, [jobs[j]], frame.data_ptr(), stream, sync=False))
+    if world > 1:
+        dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+    return mine
