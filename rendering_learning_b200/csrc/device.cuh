@@ -215,6 +215,57 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
     }
 }
 
+// "while-while" traversal (Aila & Laine 2009): the inner loop only descends inner nodes; a lane that reaches a
+// leaf parks until every lane of the warp has one (or is done), then the leaves are tested together.  ncu on the
+// if-if loop above showed primitive tests running with 2-4 of 32 lanes and the pop loop with < 3
+// (profiles/r01_ncu_k_ow_render_v1.json); here the slab tests use the FMA form (lo * inv - o * inv) and the pop
+// is a single predicated stack read — a popped node whose entry distance is now beyond tmax fails its own slab
+// test, so no cull loop is needed.
+constexpr int TRAV_END = (int)0x80000000;
+template <bool COUNT, class LeafFn>
+__device__ __forceinline__ void bvh_traverse_ww(const BvhNode* __restrict__ nodes, int n_bvh_prims, const RayPre& r,
+                                                float tmin, float tmax, LocalCount<COUNT>& lc, LeafFn leaf) {
+    if (n_bvh_prims <= 0) return;
+    int stack_node[BVH_STACK];
+    int sp = 0;
+    int node = 0;
+    const float3 oi = f3(r.o.x * r.inv_d.x, r.o.y * r.inv_d.y, r.o.z * r.inv_d.z);
+    while (node != TRAV_END) {
+        while (node >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(nodes + node);
+            float4 a = np[0], b = np[1], c = np[2];
+            int4 d = *reinterpret_cast<const int4*>(np + 3);
+            if (COUNT) lc.nodes++;
+            float t0x = fmaf(a.x, r.inv_d.x, -oi.x), t1x = fmaf(a.w, r.inv_d.x, -oi.x);
+            float t0y = fmaf(a.y, r.inv_d.y, -oi.y), t1y = fmaf(b.x, r.inv_d.y, -oi.y);
+            float t0z = fmaf(a.z, r.inv_d.z, -oi.z), t1z = fmaf(b.y, r.inv_d.z, -oi.z);
+            float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+            float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+            float u0x = fmaf(b.z, r.inv_d.x, -oi.x), u1x = fmaf(c.y, r.inv_d.x, -oi.x);
+            float u0y = fmaf(b.w, r.inv_d.y, -oi.y), u1y = fmaf(c.z, r.inv_d.y, -oi.y);
+            float u0z = fmaf(c.x, r.inv_d.z, -oi.z), u1z = fmaf(c.w, r.inv_d.z, -oi.z);
+            float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));
+            float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));
+            bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
+            int nearc = d.x, farc = d.y;
+            if (n1 < n0) { nearc = d.y; farc = d.x; }
+            if (h0 && h1) {
+                if (sp < BVH_STACK) stack_node[sp++] = farc; else lc.overflow++;
+                node = nearc;
+            } else if (h0 || h1) {
+                node = h0 ? d.x : d.y;
+            } else {
+                node = sp > 0 ? stack_node[--sp] : TRAV_END;
+            }
+        }
+        if (node != TRAV_END) {
+            tmax = leaf(~node, tmax);
+            if (tmax == -RL_INF) return;
+            node = sp > 0 ? stack_node[--sp] : TRAV_END;
+        }
+    }
+}
+
 // ---- work distribution ----------------------------------------------------------------------------------
 // jobs = pixel rectangles (x sample-chunk ranges for OW); item enumeration walks 8x4 pixel micro-tiles so
 // that the 32 lanes of a warp start on neighbouring pixels.

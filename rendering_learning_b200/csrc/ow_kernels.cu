@@ -13,6 +13,8 @@
 // RNG: Philox4x32-10 keyed by the camera seed, counter = (pixel, absolute sample, bounce, dimension) —
 // statistical parity with the reference's ChaCha8 streams, and absolute sample indices
 // keep render_from_checkpoint streams disjoint like camera.rs:162-170.
+#include <cstdlib>
+
 #include "device.cuh"
 #include "kernels.h"
 
@@ -80,8 +82,96 @@ struct OwHit {
     float b1, b2;
 };
 
-// world.hit(r, [tmin, inf)) through the LBVH.  `self_ref` is the primitive the ray starts on.
+// One primitive test of world.hit: updates `h` when the primitive is hit closer than h.t.
+// `self_ref` is the primitive the ray starts on (never re-hit at t ~ 0; a sphere only at its far root).
 template <bool COUNT>
+__device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
+                                             int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc) {
+    const float3 o = pre.o, d = pre.d;
+    int type = ref_type(ref), idx = ref_index(ref);
+    if (type == REF_SPHERE) {  // sphere.rs:34-75
+        float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
+        if (COUNT) lc.prims++;
+        float3 center = fma3(f3(dc), time, f3(c));
+        float3 oc = o - center;
+        float hb = dot(oc, d);
+        float t;
+        if (ref == self_ref) {
+            // origin lies on this sphere: the roots are 0 and -2 hb / a; only the far one is a new hit
+            t = -2.0f * hb / a_dd;
+            if (!(t > 1e-4f * fabsf(c.w) * rsqrtf(a_dd))) return;
+        } else if (fabsf(c.w) >= OW_BIG_RADIUS) {
+            // a huge sphere seen from near its surface (the r = 1000 ground of the cover scene): r^2 - |perp|^2
+            // cancels ~7 digits, more than f32 has.  One such primitive sits near the BVH root, so its
+            // quadratic is evaluated in f64 (B200 runs FP64 at half the FP32 rate; the cost is one test per ray).
+            double ox = (double)oc.x, oy = (double)oc.y, oz = (double)oc.z;
+            double dx = (double)d.x, dy = (double)d.y, dz = (double)d.z;
+            double a = dx * dx + dy * dy + dz * dz;
+            double hbd = ox * dx + oy * dy + oz * dz;
+            double cc = ox * ox + oy * oy + oz * oz - (double)c.w * (double)c.w;
+            double disc = hbd * hbd - a * cc;
+            if (disc < 0.0) return;
+            double sq = sqrt(disc);
+            t = (float)((-hbd - sq) / a);
+            if (!(t >= tmin && t <= h.t)) {
+                t = (float)((-hbd + sq) / a);
+                if (!(t >= tmin && t <= h.t)) return;
+            }
+        } else {
+            float tc = -hb / a_dd;
+            float3 perp = fma3(d, tc, oc);
+            float disc = a_dd * (c.w * c.w - dot(perp, perp));
+            if (disc < 0.0f) return;
+            float q = sqrtf(disc) / a_dd;
+            t = tc - q;
+            if (!(t >= tmin && t <= h.t)) {
+                t = tc + q;
+                if (!(t >= tmin && t <= h.t)) return;
+            }
+        }
+        if (t < h.t) {
+            h.t = t;
+            h.ref = ref;
+            return;
+        }
+        return;
+    } else if (type == REF_TRI) {  // flat/triangle.rs:60-95 (watertight test instead of the plane basis)
+        if (ref == self_ref) return;
+        float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
+        if (COUNT) lc.tris++;
+        float t, b1, b2;
+        if (tri_hit(pre, f3(p0), f3(p1), f3(p2), &t, &b1, &b2) && t >= tmin && t < h.t) {
+            h.t = t;
+            h.ref = ref;
+            h.b1 = b1;
+            h.b2 = b2;
+            return;
+        }
+        return;
+    } else {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
+        if (ref == self_ref) return;
+        const OwQuad& qd = sc.quads[idx];
+        float4 n4 = qd.n, q4 = qd.q;
+        if (COUNT) lc.prims++;
+        float denom = dot(f3(n4), d);
+        if (fabsf(denom) < 1e-8f) return;
+        float t = (q4.w - dot(f3(n4), o)) / denom;
+        if (!(t >= tmin && t < h.t)) return;
+        float3 ph = fma3(d, t, o) - f3(q4);
+        float3 w = f3(qd.w);
+        float alpha = dot(w, cross(ph, f3(qd.v)));
+        float beta = dot(w, cross(f3(qd.u), ph));
+        if (!(0.0f <= alpha && alpha <= 1.0f && 0.0f <= beta && beta <= 1.0f)) return;
+        h.t = t;
+        h.ref = ref;
+        h.b1 = alpha;
+        h.b2 = beta;
+        return;
+    }
+}
+
+// world.hit(r, [tmin, inf)) through the LBVH (callback form; used by rl_trace_batch and the v1 kernel).
+template <bool COUNT, int TRAV = 0>
 __device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3 d, float time, int self_ref, float tmin,
                                             LocalCount<COUNT>& lc) {
     OwHit h;
@@ -93,88 +183,12 @@ __device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3
     const float a_dd = dot(d, d);
     OwHit* hp = &h;
     LocalCount<COUNT>& lcr = lc;
-    bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, RL_INF, lc, [&](int ref, float tmax) -> float {
-        int type = ref_type(ref), idx = ref_index(ref);
-        if (type == REF_SPHERE) {  // sphere.rs:34-75
-            float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
-            if (COUNT) lcr.prims++;
-            float3 center = fma3(f3(dc), time, f3(c));
-            float3 oc = o - center;
-            float hb = dot(oc, d);
-            float t;
-            if (ref == self_ref) {
-                // origin lies on this sphere: the roots are 0 and -2 hb / a; only the far one is a new hit
-                t = -2.0f * hb / a_dd;
-                if (!(t > 1e-4f * fabsf(c.w) * rsqrtf(a_dd))) return tmax;
-            } else if (fabsf(c.w) >= OW_BIG_RADIUS) {
-                // a huge sphere seen from near its surface (the r = 1000 ground of the cover scene): r^2 - |perp|^2
-                // cancels ~7 digits, more than f32 has.  One such primitive sits near the BVH root, so its
-                // quadratic is evaluated in f64 (B200 runs FP64 at half the FP32 rate; the cost is one test per ray).
-                double ox = (double)oc.x, oy = (double)oc.y, oz = (double)oc.z;
-                double dx = (double)d.x, dy = (double)d.y, dz = (double)d.z;
-                double a = dx * dx + dy * dy + dz * dz;
-                double hbd = ox * dx + oy * dy + oz * dz;
-                double cc = ox * ox + oy * oy + oz * oz - (double)c.w * (double)c.w;
-                double disc = hbd * hbd - a * cc;
-                if (disc < 0.0) return tmax;
-                double sq = sqrt(disc);
-                t = (float)((-hbd - sq) / a);
-                if (!(t >= tmin && t <= tmax)) {
-                    t = (float)((-hbd + sq) / a);
-                    if (!(t >= tmin && t <= tmax)) return tmax;
-                }
-            } else {
-                float tc = -hb / a_dd;
-                float3 perp = fma3(d, tc, oc);
-                float disc = a_dd * (c.w * c.w - dot(perp, perp));
-                if (disc < 0.0f) return tmax;
-                float q = sqrtf(disc) / a_dd;
-                t = tc - q;
-                if (!(t >= tmin && t <= tmax)) {
-                    t = tc + q;
-                    if (!(t >= tmin && t <= tmax)) return tmax;
-                }
-            }
-            if (t < tmax) {
-                hp->t = t;
-                hp->ref = ref;
-                return t;
-            }
-            return tmax;
-        } else if (type == REF_TRI) {  // flat/triangle.rs:60-95 (watertight test instead of the plane basis)
-            if (ref == self_ref) return tmax;
-            float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
-            if (COUNT) lcr.tris++;
-            float t, b1, b2;
-            if (tri_hit(pre, f3(p0), f3(p1), f3(p2), &t, &b1, &b2) && t >= tmin && t < tmax) {
-                hp->t = t;
-                hp->ref = ref;
-                hp->b1 = b1;
-                hp->b2 = b2;
-                return t;
-            }
-            return tmax;
-        } else {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
-            if (ref == self_ref) return tmax;
-            const OwQuad& qd = sc.quads[idx];
-            float4 n4 = qd.n, q4 = qd.q;
-            if (COUNT) lcr.prims++;
-            float denom = dot(f3(n4), d);
-            if (fabsf(denom) < 1e-8f) return tmax;
-            float t = (q4.w - dot(f3(n4), o)) / denom;
-            if (!(t >= tmin && t < tmax)) return tmax;
-            float3 ph = fma3(d, t, o) - f3(q4);
-            float3 w = f3(qd.w);
-            float alpha = dot(w, cross(ph, f3(qd.v)));
-            float beta = dot(w, cross(f3(qd.u), ph));
-            if (!(0.0f <= alpha && alpha <= 1.0f && 0.0f <= beta && beta <= 1.0f)) return tmax;
-            hp->t = t;
-            hp->ref = ref;
-            hp->b1 = alpha;
-            hp->b2 = beta;
-            return t;
-        }
-    });
+    auto leaf = [&](int ref, float tmax) -> float {
+        ow_leaf_test<COUNT>(sc, ref, pre, a_dd, time, self_ref, tmin, *hp, lcr);
+        return hp->t;
+    };
+    if (TRAV == 1) bvh_traverse_ww<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, RL_INF, lc, leaf);
+    else bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, RL_INF, lc, leaf);
     return h;
 }
 
@@ -188,10 +202,24 @@ struct Path {
 };
 
 // hit record + material evaluation for one bounce; returns false when the path ends
+__device__ __forceinline__ float ow_tmin(const Path& p) {
+    return fmaf(1e-5f, max_abs(p.o), 1e-6f) * rsqrtf(dot(p.d, p.d));
+}
+
 template <bool COUNT>
+__device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, Path& p, const OwHit& h, uint4 rnd,
+                                         LocalCount<COUNT>& lc);
+
+template <bool COUNT, int TRAV>
 __device__ __forceinline__ bool ow_bounce(const DevScene& sc, const OwCam& cam, Path& p, uint4 rnd, LocalCount<COUNT>& lc) {
-    float tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f) * rsqrtf(dot(p.d, p.d));
-    OwHit h = ow_closest<COUNT>(sc, p.o, p.d, p.time, p.self_ref, tmin, lc);
+    OwHit h = ow_closest<COUNT, TRAV>(sc, p.o, p.d, p.time, p.self_ref, ow_tmin(p), lc);
+    return ow_shade<COUNT>(sc, cam, p, h, rnd, lc);
+}
+
+// hit record + emitted + scatter for the closest hit `h` of path `p` (camera.rs:246-258)
+template <bool COUNT>
+__device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, Path& p, const OwHit& h, uint4 rnd,
+                                         LocalCount<COUNT>& lc) {
     if (h.ref < 0) {  // camera.rs:256-258
         p.rad = p.rad + p.thr * cam.background;
         return false;
@@ -319,8 +347,8 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
     p.self_ref = -1;
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_ow_render(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
+template <bool COUNT, int TRAV, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                    unsigned long long* __restrict__ queue, Counters* counters) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
@@ -387,11 +415,186 @@ __global__ void __launch_bounds__(256) k_ow_render(DevScene sc, OwCam cam, JobTa
             unsigned pixel = (unsigned)(y * cam.width + x);
             unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
             uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
-            bool cont = ow_bounce<COUNT>(sc, cam, p, rnd, lc);
+            bool cont = ow_bounce<COUNT, TRAV>(sc, cam, p, rnd, lc);
             if (!cont) {
                 acc = acc + p.rad;  // samples are folded in order (camera.rs:174)
                 alive = false;
                 s++;
+            }
+        }
+    }
+    lc.flush(counters);
+}
+
+// ---- v2: warp-scheduled state machine -----------------------------------------------------------------------
+// ncu on v1 (profiles/r01_ncu_k_ow_render_v1.json) shows 11 of 32 lanes active per issued instruction: every
+// lane runs its own traversal loop, leaf tests sit inside that loop, and a bounce ends only when the slowest
+// lane of the warp is done.  v2 keeps the per-lane persistent paths but lets the WARP choose, every iteration,
+// one of three actions from ballots of the lane states:
+//     inner step : lanes at an inner BVH node visit it (two slab tests, push / pop)
+//     leaf step  : lanes parked at a leaf run the primitive test           (postponed until enough lanes wait)
+//     service    : lanes whose traversal finished shade + scatter, dead paths are regenerated, finished items
+//                  retired and refilled from the queue                       (postponed until enough lanes wait)
+// so each action runs with a popc-checked minimum number of active lanes instead of whatever divergence leaves.
+constexpr int TRAV_DONE = (int)0x80000000;
+enum { PH_NEED = 0, PH_TRAV = 1, PH_SHADE = 2, PH_IDLE = 3 };
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256, 2) k_ow_render2(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
+                                                       unsigned long long* __restrict__ queue, Counters* counters,
+                                                       int svc_num, int leaf_num) {
+    LocalCount<COUNT> lc;
+    const unsigned lane = threadIdx.x & 31;
+    const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
+    // item
+    bool has_item = false, queue_empty = false;
+    int x = 0, y = 0, chunk = 0, s = 0, s_end = 0;
+    float3 acc = f3(0.0f, 0.0f, 0.0f);
+    // path
+    Path p;
+    p.depth = 0;
+    // traversal
+    RayPre pre = make_pre(f3(0.0f, 0.0f, 0.0f), f3(0.0f, 0.0f, 1.0f));
+    float a_dd = 1.0f, tmin = 0.0f;
+    OwHit hit;
+    hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
+    int node = TRAV_DONE, sp = 0;
+    int stack_node[BVH_STACK];
+    float stack_t[BVH_STACK];
+    int phase = PH_NEED;
+
+    auto start_traversal = [&]() {
+        pre = make_pre(p.o, p.d);
+        a_dd = dot(p.d, p.d);
+        tmin = ow_tmin(p);
+        hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
+        sp = 0;
+        node = sc.n_bvh_prims > 0 ? 0 : TRAV_DONE;
+        phase = node == TRAV_DONE ? PH_SHADE : PH_TRAV;
+        if (COUNT) lc.rays++;
+    };
+    auto pop = [&]() {
+        node = TRAV_DONE;
+        while (sp > 0) {
+            sp--;
+            if (stack_t[sp] <= slack(hit.t)) { node = stack_node[sp]; break; }
+        }
+        if (node == TRAV_DONE) phase = PH_SHADE;
+    };
+
+    while (true) {
+        const bool trav = phase == PH_TRAV;
+        const unsigned m_inner = __ballot_sync(0xffffffffu, trav && node >= 0);
+        const unsigned m_leaf = __ballot_sync(0xffffffffu, trav && node < 0);
+        const unsigned m_wait = __ballot_sync(0xffffffffu, phase == PH_NEED || phase == PH_SHADE);
+        if ((m_inner | m_leaf | m_wait) == 0u) break;
+        const int n_inner = __popc(m_inner), n_leaf = __popc(m_leaf), n_wait = __popc(m_wait);
+        const int n_trav = n_inner + n_leaf;
+        if (n_trav == 0 || n_wait >= max(1, ((n_trav + n_wait) * svc_num) >> 5)) {
+            // ---------------- service: shade, retire, refill, regenerate ----------------
+            if (phase == PH_SHADE) {
+                unsigned pixel = (unsigned)(y * cam.width + x);
+                unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
+                uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
+                if (ow_shade<COUNT>(sc, cam, p, hit, rnd, lc)) {
+                    start_traversal();
+                } else {
+                    acc = acc + p.rad;  // samples are folded in order (camera.rs:174)
+                    s++;
+                    phase = PH_NEED;
+                }
+            }
+            if (phase == PH_NEED && has_item && s == s_end) {
+                size_t idx = (((size_t)chunk * cam.height + y) * cam.width + x) * 3;
+                partial[idx + 0] = acc.x;
+                partial[idx + 1] = acc.y;
+                partial[idx + 2] = acc.z;
+                has_item = false;
+            }
+            const bool need = phase == PH_NEED && !has_item && !queue_empty;
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask) {  // one warp-aggregated pop for all requesting lanes
+                int leader = __ffs(mask) - 1;
+                unsigned long long base = 0;
+                if (lane == (unsigned)leader) base = atomicAdd(queue, (unsigned long long)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need) {
+                    long long item = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
+                    if (item >= jt.n_items) {
+                        queue_empty = true;
+                    } else {
+                        int j = find_job(jt, item);
+                        rl_job job = jt_job(jt, j);
+                        long long local = item - jt_prefix(jt, j);
+                        int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
+                        long long pp = padded_pixels(w, hgt);
+                        int ck = (int)(local / pp);
+                        int px, py;
+                        tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
+                        if (px < w && py < hgt) {
+                            x = job.x0 + px;
+                            y = job.y0 + py;
+                            chunk = job.chunk_begin + ck;
+                            chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                            if (cam.max_depth <= 0) s = s_end;  // depth 0: every sample is black
+                            acc = f3(0.0f, 0.0f, 0.0f);
+                            has_item = true;
+                        }
+                    }
+                }
+            }
+            if (phase == PH_NEED) {
+                if (has_item && s < s_end) {
+                    ow_camera_ray(cam, x, y, (unsigned)(cam.first_sample + s), p);
+                    start_traversal();
+                } else if (!has_item && queue_empty) {
+                    phase = PH_IDLE;
+                }
+            }
+        } else if (n_inner == 0 || n_leaf >= max(1, (n_trav * leaf_num) >> 5)) {
+            // ---------------- leaf step ----------------
+            if (trav && node < 0) {
+                ow_leaf_test<COUNT>(sc, ~node, pre, a_dd, p.time, p.self_ref, tmin, hit, lc);
+                pop();
+            }
+        } else {
+            // ---------------- inner step ----------------
+            if (trav && node >= 0) {
+                const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+                float4 a = np[0], b = np[1], c = np[2];
+                int4 d = *reinterpret_cast<const int4*>(np + 3);
+                if (COUNT) lc.nodes++;
+                const float tmax = hit.t;
+                float t0x = (a.x - pre.o.x) * pre.inv_d.x, t1x = (a.w - pre.o.x) * pre.inv_d.x;
+                float t0y = (a.y - pre.o.y) * pre.inv_d.y, t1y = (b.x - pre.o.y) * pre.inv_d.y;
+                float t0z = (a.z - pre.o.z) * pre.inv_d.z, t1z = (b.y - pre.o.z) * pre.inv_d.z;
+                float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+                float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+                float u0x = (b.z - pre.o.x) * pre.inv_d.x, u1x = (c.y - pre.o.x) * pre.inv_d.x;
+                float u0y = (b.w - pre.o.y) * pre.inv_d.y, u1y = (c.z - pre.o.y) * pre.inv_d.y;
+                float u0z = (c.x - pre.o.z) * pre.inv_d.z, u1z = (c.w - pre.o.z) * pre.inv_d.z;
+                float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));
+                float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));
+                bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
+                if (h0 && h1) {
+                    int nearc = d.x, farc = d.y;
+                    float tf = n1;
+                    if (n1 < n0) { nearc = d.y; farc = d.x; tf = n0; }
+                    if (sp < BVH_STACK) {
+                        stack_node[sp] = farc;
+                        stack_t[sp] = tf;
+                        sp++;
+                    } else {
+                        lc.overflow++;
+                    }
+                    node = nearc;
+                } else if (h0) {
+                    node = d.x;
+                } else if (h1) {
+                    node = d.y;
+                } else {
+                    pop();
+                }
             }
         }
     }
@@ -489,6 +692,11 @@ static OwCam make_cam(const rl_ow_camera* p, uint32_t first_sample) {
     return c;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
                              float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
                              int sm_count, cudaStream_t stream) {
@@ -496,17 +704,42 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     OwCam c = make_cam(cam, first_sample);
     cudaError_t e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
+    // Kernel variants stay selectable for A/B profiling (DESIGN.md §"OW kernel variants", profiles/r01_ncu_k_ow_render_*):
+    //   RL_OW_KERNEL_V=1  per-lane if-if traversal loop                     (first version)
+    //   RL_OW_KERNEL_V=2  warp-scheduled state machine (ballot/popc picks inner / leaf / service steps)
+    //   RL_OW_KERNEL_V=3  while-while traversal, FMA slabs, cull-free pop   (default; RL_OW_MINB = blocks per SM)
+    static const int variant = env_int("RL_OW_KERNEL_V", 3);
+    static const int svc_num = env_int("RL_OW_SVC", 8), leaf_num = env_int("RL_OW_LEAF", 12);
     int per_sm = 0;
-    if (instrumented) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render<true>, 256, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render<false>, 256, 0);
+    typedef void (*K1)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*);
+    K1 k1 = nullptr;
+    static const int minb = env_int("RL_OW_MINB", 4);
+    if (variant == 1) k1 = instrumented ? (K1)k_ow_render<true, 0, 2> : (K1)k_ow_render<false, 0, 2>;
+    if (variant == 3) {
+        if (minb == 4) k1 = instrumented ? (K1)k_ow_render<true, 1, 4> : (K1)k_ow_render<false, 1, 4>;
+        else if (minb == 3) k1 = instrumented ? (K1)k_ow_render<true, 1, 3> : (K1)k_ow_render<false, 1, 3>;
+        else k1 = instrumented ? (K1)k_ow_render<true, 1, 2> : (K1)k_ow_render<false, 1, 2>;
+    }
+    if (k1) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, 256, 0);
+    } else {
+        if (instrumented) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render2<true>, 256, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render2<false>, 256, 0);
+    }
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long want = (jt.n_items + 255) / 256;
     long long grid = (long long)sm_count * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    if (instrumented) k_ow_render<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters);
-    else k_ow_render<false><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters);
+    if (k1) {
+        k1<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters);
+    } else {
+        if (instrumented)
+            k_ow_render2<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num);
+        else
+            k_ow_render2<false><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num);
+    }
     return cudaGetLastError();
 }
 
