@@ -271,8 +271,14 @@ def main():
         ctx.set_instrumented(False)
         counter = [0]
 
+        mgpu = os.environ.get("RL_MGPU", "device")  # "device": NVLink-atomic queue in rank 0's HBM; "store": c10d-store queue
+        shared = world_size > 1 and mgpu == "device" and rd.setup_shared_queue(ctx)
+
         def step(i):
             counter[0] += 1
+            if shared:
+                rd.render_ow_shared_queue(ctx, cam, 0, partial, frame, nc, H, W)
+                return [0]
             return rd.render_ow_distributed(ctx, cam, 0, jobs, partial, frame, f"s{i}_{counter[0]}")
 
         def kernel_probe():
@@ -307,6 +313,7 @@ def main():
         st_i = ctx.render_rtc_device(cam, 1, [(0, 0, W, H, 0, 1)], frame.data_ptr(), stream).as_dict() if rank == 0 else None
         ctx.set_instrumented(False)
         counter = [0]
+        shared = False
 
         def step(i):
             counter[0] += 1
@@ -414,8 +421,10 @@ def main():
             "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "image": [W, H], "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"{len(jobs)} tile x sample-chunk jobs, dynamic queue, {world_size} rank(s), "
-                                      "NCCL sum-gather to rank 0" if world_size > 1 else "1 rank, persistent warps"},
+                       "parallelism": (("one persistent launch per GPU; warps pop (pixel x sample-chunk) items from ONE counter in "
+                                        "rank 0's HBM with system-scope atomics over NVLink (CUDA IPC)" if (wl["kind"] == "ow" and shared)
+                                        else f"{len(jobs)} tile x sample-chunk jobs from a c10d-store queue") +
+                                       f", {world_size} ranks, NCCL sum-gather to rank 0") if world_size > 1 else "1 rank, persistent warps"},
             "samples_per_s": samples / (ms_per_step * 1e-3), "rays_per_step": rays, "samples_per_step": samples,
             "wall_s_timed_region": t_wall, "step_ms": step_ms,
             "clocks": clocks, "gpu_launches": total_launches,

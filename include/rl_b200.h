@@ -281,6 +281,19 @@ int rl_render_ow_device(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sam
 int rl_ow_reduce_device(rl_ctx* ctx, const rl_ow_camera* cam, const void* d_partial,
                         void* d_out_rgb_sum, void* stream);
 
+/* Cross-GPU dynamic tile queue: ONE 64-bit counter in the exporting ctx's HBM, mapped into the
+ * other ranks' processes with CUDA IPC and popped with system-scope atomics over NVLink by the persistent
+ * render kernels, 32 work items (pixel x sample-chunk) per warp-aggregated pop — no host in the loop.
+ *   owner : rl_queue_export -> 64-byte handle (ship it to the peers), rl_queue_reset before every render
+ *   peers : rl_queue_import
+ *   all   : rl_render_ow_shared — asynchronous; every rank passes the SAME job list and writes the items it
+ *           popped into its own d_partial (zero elsewhere), which is then sum-gathered with NCCL. */
+int rl_queue_export(rl_ctx* ctx, void* handle64);
+int rl_queue_import(rl_ctx* ctx, const void* handle64);
+int rl_queue_reset(rl_ctx* ctx, void* stream);
+int rl_render_ow_shared(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs,
+                        int32_t n_jobs, void* d_partial, void* stream);
+
 /* enable/disable the instrumented (counting) kernel variants; counters cost atomics, so timing runs
  * keep them off and a separate instrumented pass with the same seed fills rl_stats. */
 int rl_set_instrumented(rl_ctx* ctx, int enabled);

@@ -182,6 +182,10 @@ SYMBOLS = {
                                       C.c_int32, _P, _P, C.POINTER(rl_stats)]),
     "rl_ow_reduce_device": (C.c_int, [_P, C.POINTER(rl_ow_camera), _P, _P, _P]),
     "rl_set_instrumented": (C.c_int, [_P, C.c_int]),
+    "rl_queue_export": (C.c_int, [_P, C.c_void_p]),
+    "rl_queue_import": (C.c_int, [_P, C.c_void_p]),
+    "rl_queue_reset": (C.c_int, [_P, _P]),
+    "rl_render_ow_shared": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(rl_job), C.c_int32, _P, _P]),
 }
 
 

@@ -163,6 +163,24 @@ class Context:
                                                  C.byref(stats) if sync else None))
         return stats
 
+    # ---- cross-GPU queue (CUDA IPC + NVLink atomics) -----------------------------------------------
+    def queue_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.rl_queue_export(self.h, buf))
+        return buf.raw
+
+    def queue_import(self, handle: bytes):
+        buf = C.create_string_buffer(handle, 64)
+        self._check(self.lib.rl_queue_import(self.h, buf))
+
+    def queue_reset(self, stream: int = 0):
+        self._check(self.lib.rl_queue_reset(self.h, C.c_void_p(stream)))
+
+    def render_ow_shared(self, cam, first_sample, jobs, d_partial_ptr: int, stream: int = 0):
+        arr = self._jobs(jobs)
+        self._check(self.lib.rl_render_ow_shared(self.h, C.byref(cam), C.c_uint32(first_sample), arr, len(jobs),
+                                                 C.c_void_p(d_partial_ptr), C.c_void_p(stream)))
+
     def ow_reduce_device(self, cam, d_partial_ptr: int, d_out_ptr: int, stream: int = 0):
         self._check(self.lib.rl_ow_reduce_device(self.h, C.byref(cam), C.c_void_p(d_partial_ptr),
                                                  C.c_void_p(d_out_ptr), C.c_void_p(stream)))

@@ -63,6 +63,10 @@ struct rl_ctx {
     int upload_launches = 0;
     // work buffers
     DevBuf counters, queue, jobs, prefix, frame, partial, rays, hits;
+    // cross-GPU queue (CUDA IPC): the owner allocates it, peers map it
+    DevBuf shared_queue_own;
+    unsigned long long* shared_queue = nullptr;
+    bool shared_queue_imported = false;
 };
 
 #define CK(ctx, call)                                                                           \
@@ -144,6 +148,8 @@ void rl_destroy(rl_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->shared_queue_imported && c->shared_queue) cudaIpcCloseMemHandle(c->shared_queue);
+    c->shared_queue_own.release();
     DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
                      &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
@@ -533,6 +539,61 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
     st.samples = samples;
     *stats = st;
     return rc;
+}
+
+int rl_queue_export(rl_ctx* c, void* handle64) {
+    if (!c || !handle64) return RL_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(c, cudaSetDevice(c->device));
+    if (!c->shared_queue_own.p) {
+        CK(c, c->shared_queue_own.reserve(256));
+        CK(c, cudaMemset(c->shared_queue_own.p, 0, 256));
+    }
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, c->shared_queue_own.p));
+    memcpy(handle64, &h, sizeof(h));
+    c->shared_queue = c->shared_queue_own.as<unsigned long long>();
+    c->shared_queue_imported = false;
+    return RL_OK;
+}
+
+int rl_queue_import(rl_ctx* c, const void* handle64) {
+    if (!c || !handle64) return RL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->shared_queue = (unsigned long long*)p;
+    c->shared_queue_imported = true;
+    return RL_OK;
+}
+
+int rl_queue_reset(rl_ctx* c, void* stream) {
+    if (!c) return RL_E_INVALID;
+    if (!c->shared_queue || c->shared_queue_imported) return fail(c, RL_E_INVALID, "only the exporting ctx resets the shared queue");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CK(c, cudaMemsetAsync(c->shared_queue, 0, sizeof(unsigned long long), s));
+    return RL_OK;
+}
+
+int rl_render_ow_shared(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs, int32_t n_jobs,
+                        void* d_partial, void* stream) {
+    if (!c || !cam || !d_partial) return RL_E_INVALID;
+    if (!c->has_scene || c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_NO_SCENE, "no OW scene uploaded");
+    if (!c->shared_queue) return fail(c, RL_E_INVALID, "no shared queue: call rl_queue_export / rl_queue_import first");
+    if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0) || cam->max_depth < 0)
+        return fail(c, RL_E_INVALID, "bad camera parameters");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
+    JobTable jt;
+    int rc = make_job_table(c, jobs, n_jobs, cam->image_width, H, nc, true, s, &jt);
+    if (rc != RL_OK) return rc;
+    CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->shared_queue, c->counters.as<Counters>(),
+                           false, c->sm_count, s, true));
+    return RL_OK;
 }
 
 int rl_ow_reduce_device(rl_ctx* c, const rl_ow_camera* cam, const void* d_partial, void* d_out, void* stream) {

@@ -19,7 +19,7 @@ int ow_num_chunks(int spp);
 int ow_image_height(const rl_ow_camera* c);
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
                              float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
-                             int sm_count, cudaStream_t stream);
+                             int sm_count, cudaStream_t stream, bool shared_queue = false);
 cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream);
 cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t n, rl_hit* d_hits, Counters* d_counters,
                             bool instrumented, cudaStream_t stream);

@@ -349,7 +349,7 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
 
 template <bool COUNT, int TRAV, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
-                                                   unsigned long long* __restrict__ queue, Counters* counters) {
+                                                   unsigned long long* __restrict__ queue, Counters* counters, int sys_queue) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
     const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
@@ -373,7 +373,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
         if (mask) {
             int leader = __ffs(mask) - 1;
             unsigned long long base = 0;
-            if (lane == (unsigned)leader) base = atomicAdd(queue, (unsigned long long)__popc(mask));
+            if (lane == (unsigned)leader) {
+                // sys_queue: ONE counter in rank 0's HBM shared by every GPU of the box (CUDA IPC mapping, popped
+                // over NVLink) — a dynamic tile queue at warp granularity with no host in the loop
+                base = sys_queue ? atomicAdd_system(queue, (unsigned long long)__popc(mask))
+                                 : atomicAdd(queue, (unsigned long long)__popc(mask));
+            }
             base = __shfl_sync(0xffffffffu, base, leader);
             if (need) {
                 long long item = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
@@ -442,7 +447,7 @@ enum { PH_NEED = 0, PH_TRAV = 1, PH_SHADE = 2, PH_IDLE = 3 };
 template <bool COUNT>
 __global__ void __launch_bounds__(256, 2) k_ow_render2(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                        unsigned long long* __restrict__ queue, Counters* counters,
-                                                       int svc_num, int leaf_num) {
+                                                       int svc_num, int leaf_num, int sys_queue) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
     const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
@@ -516,7 +521,12 @@ __global__ void __launch_bounds__(256, 2) k_ow_render2(DevScene sc, OwCam cam, J
             if (mask) {  // one warp-aggregated pop for all requesting lanes
                 int leader = __ffs(mask) - 1;
                 unsigned long long base = 0;
-                if (lane == (unsigned)leader) base = atomicAdd(queue, (unsigned long long)__popc(mask));
+                if (lane == (unsigned)leader) {
+                // sys_queue: ONE counter in rank 0's HBM shared by every GPU of the box (CUDA IPC mapping, popped
+                // over NVLink) — a dynamic tile queue at warp granularity with no host in the loop
+                base = sys_queue ? atomicAdd_system(queue, (unsigned long long)__popc(mask))
+                                 : atomicAdd(queue, (unsigned long long)__popc(mask));
+            }
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (need) {
                     long long item = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
@@ -699,11 +709,13 @@ static int env_int(const char* name, int dflt) {
 
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
                              float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
-                             int sm_count, cudaStream_t stream) {
+                             int sm_count, cudaStream_t stream, bool shared_queue) {
     if (jt.n_items <= 0) return cudaSuccess;
     OwCam c = make_cam(cam, first_sample);
-    cudaError_t e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream);
+    cudaError_t e = cudaSuccess;
+    if (!shared_queue) e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream);  // the owner resets a shared queue
     if (e != cudaSuccess) return e;
+    const int sysq = shared_queue ? 1 : 0;
     // Kernel variants stay selectable for A/B profiling (DESIGN.md §"OW kernel variants", profiles/r01_ncu_k_ow_render_*):
     //   RL_OW_KERNEL_V=1  per-lane if-if traversal loop                     (first version)
     //   RL_OW_KERNEL_V=2  warp-scheduled state machine (ballot/popc picks inner / leaf / service steps)
@@ -711,7 +723,7 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     static const int variant = env_int("RL_OW_KERNEL_V", 3);
     static const int svc_num = env_int("RL_OW_SVC", 8), leaf_num = env_int("RL_OW_LEAF", 12);
     int per_sm = 0;
-    typedef void (*K1)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*);
+    typedef void (*K1)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int);
     K1 k1 = nullptr;
     static const int minb = env_int("RL_OW_MINB", 4);
     if (variant == 1) k1 = instrumented ? (K1)k_ow_render<true, 0, 2> : (K1)k_ow_render<false, 0, 2>;
@@ -730,15 +742,15 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     if (per_sm < 1) per_sm = 1;
     long long want = (jt.n_items + 255) / 256;
     long long grid = (long long)sm_count * per_sm;
-    if (grid > want) grid = want;
+    if (grid > want && !shared_queue) grid = want;
     if (grid < 1) grid = 1;
     if (k1) {
-        k1<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters);
+        k1<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq);
     } else {
         if (instrumented)
-            k_ow_render2<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num);
+            k_ow_render2<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num, sysq);
         else
-            k_ow_render2<false><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num);
+            k_ow_render2<false><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num, sysq);
     }
     return cudaGetLastError();
 }

@@ -112,6 +112,48 @@ def render_ow_distributed(ctx, cam, first_sample: int, jobs: Sequence[Job], part
     return mine
 
 
+def setup_shared_queue(ctx) -> bool:
+    """Map rank 0's work counter into every rank (CUDA IPC).  Returns False when there is a single rank."""
+    import torch.distributed as dist
+    rank, world = _rank_world()
+    if world == 1:
+        return False
+    box = [ctx.queue_export() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        ctx.queue_import(box[0])
+    dist.barrier()
+    return True
+
+
+def render_ow_shared_queue(ctx, cam, first_sample: int, partial, out, n_chunks: int, height: int, width: int):
+    """OW render with the cross-GPU device queue: one persistent launch per GPU, warps of every GPU pop
+    (pixel x sample-chunk) items from rank 0's counter over NVLink; NCCL sum-gathers the partial sums."""
+    import torch
+    import torch.distributed as dist
+    rank, world = _rank_world()
+    stream = current_stream_handle()
+    partial.zero_()
+    if rank == 0:
+        ctx.queue_reset(stream)
+    # stream-ordered rendezvous: no rank pops before the owner's reset has executed
+    dist.all_reduce(_token(partial.device))
+    ctx.render_ow_shared(cam, first_sample, [(0, 0, width, height, 0, n_chunks)], partial.data_ptr(), stream)
+    dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ctx.ow_reduce_device(cam, partial.data_ptr(), out.data_ptr(), stream)
+
+
+_tokens = {}
+
+
+def _token(device):
+    import torch
+    if device not in _tokens:
+        _tokens[device] = torch.zeros(1, dtype=torch.float32, device=device)
+    return _tokens[device]
+
+
 def render_rtc_distributed(ctx, cam, aa: int, jobs: Sequence[Job], frame, step_key: str, store=None,
                            static: bool = True):
     """One RTC render sharded over the ranks; frame: [H, W, 3] f32 device tensor (complete on rank 0)."""
