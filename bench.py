@@ -214,6 +214,15 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, args.workload)
 
+    # Libraries chat on stdout (NCCL prints its version there); the contract is ONE JSON line, so everything
+    # else goes to stderr and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from rendering_learning_b200 import Context, ow, rtc
@@ -271,11 +280,18 @@ def main():
         ctx.set_instrumented(False)
         counter = [0]
 
-        mgpu = os.environ.get("RL_MGPU", "device")  # "device": NVLink-atomic queue in rank 0's HBM; "store": c10d-store queue
-        shared = world_size > 1 and mgpu == "device" and rd.setup_shared_queue(ctx)
+        # RL_MGPU: "fused"  = NVLink-atomic queue + partial sums stored straight into rank 0's HBM (default)
+        #          "device" = NVLink-atomic queue, NCCL sum-gather of the partial sums
+        #          "store"  = c10d-store job queue, NCCL sum-gather
+        mgpu = os.environ.get("RL_MGPU", "fused")
+        shared = world_size > 1 and mgpu in ("device", "fused") and rd.setup_shared_queue(
+            ctx, partial.numel() * 4 if mgpu == "fused" else 0)
 
         def step(i):
             counter[0] += 1
+            if shared and mgpu == "fused":
+                rd.render_ow_fused(ctx, cam, 0, frame, nc, H, W)
+                return [0]
             if shared:
                 rd.render_ow_shared_queue(ctx, cam, 0, partial, frame, nc, H, W)
                 return [0]
@@ -313,7 +329,7 @@ def main():
         st_i = ctx.render_rtc_device(cam, 1, [(0, 0, W, H, 0, 1)], frame.data_ptr(), stream).as_dict() if rank == 0 else None
         ctx.set_instrumented(False)
         counter = [0]
-        shared = False
+        shared, mgpu = False, "static"
 
         def step(i):
             counter[0] += 1
@@ -422,9 +438,12 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "image": [W, H], "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": (("one persistent launch per GPU; warps pop (pixel x sample-chunk) items from ONE counter in "
-                                        "rank 0's HBM with system-scope atomics over NVLink (CUDA IPC)" if (wl["kind"] == "ow" and shared)
-                                        else f"{len(jobs)} tile x sample-chunk jobs from a c10d-store queue") +
-                                       f", {world_size} ranks, NCCL sum-gather to rank 0") if world_size > 1 else "1 rank, persistent warps"},
+                                        "rank 0's HBM with system-scope atomics over NVLink (CUDA IPC); " +
+                                        ("partial sums stored straight into rank 0's HBM over NVLink (fused gather)"
+                                         if mgpu == "fused" else "NCCL sum-gather to rank 0")
+                                        if (wl["kind"] == "ow" and shared)
+                                        else f"{len(jobs)} tile x sample-chunk jobs from a c10d-store queue, NCCL sum-gather to rank 0") +
+                                       f", {world_size} ranks") if world_size > 1 else "1 rank, persistent warps"},
             "samples_per_s": samples / (ms_per_step * 1e-3), "rays_per_step": rays, "samples_per_step": samples,
             "wall_s_timed_region": t_wall, "step_ms": step_ms,
             "clocks": clocks, "gpu_launches": total_launches,
@@ -460,7 +479,7 @@ def main():
         line["cpu_baseline"] = {"value": v if v is not None else sps / 1e6, "unit": "Mrays/s" if v is not None else "Mpixels/s",
                                 "cores": host_cores(), "kind": "port", "sample": what, "seconds": dt,
                                 "samples_per_s": sps}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world_size > 1:
         dist.destroy_process_group()
 

@@ -291,6 +291,12 @@ int rl_ow_reduce_device(rl_ctx* ctx, const rl_ow_camera* cam, const void* d_part
 int rl_queue_export(rl_ctx* ctx, void* handle64);
 int rl_queue_import(rl_ctx* ctx, const void* handle64);
 int rl_queue_reset(rl_ctx* ctx, void* stream);
+/* Fused gather: the owner also exports its [n_chunks][H][W][3] partial-sum buffer; with d_partial == NULL
+ * rl_render_ow_shared stores every finished item straight into the OWNER's HBM over NVLink (each slot is
+ * written exactly once, by whichever GPU popped it), so no separate framebuffer collective is needed — only
+ * a rendezvous before rl_ow_reduce_device(d_partial = NULL) folds the chunks on the owner. */
+int rl_partial_export(rl_ctx* ctx, uint64_t bytes, void* handle64);
+int rl_partial_import(rl_ctx* ctx, const void* handle64);
 int rl_render_ow_shared(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs,
                         int32_t n_jobs, void* d_partial, void* stream);
 

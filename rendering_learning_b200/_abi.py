@@ -185,6 +185,8 @@ SYMBOLS = {
     "rl_queue_export": (C.c_int, [_P, C.c_void_p]),
     "rl_queue_import": (C.c_int, [_P, C.c_void_p]),
     "rl_queue_reset": (C.c_int, [_P, _P]),
+    "rl_partial_export": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
+    "rl_partial_import": (C.c_int, [_P, C.c_void_p]),
     "rl_render_ow_shared": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(rl_job), C.c_int32, _P, _P]),
 }
 

@@ -173,6 +173,15 @@ class Context:
         buf = C.create_string_buffer(handle, 64)
         self._check(self.lib.rl_queue_import(self.h, buf))
 
+    def partial_export(self, nbytes: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.rl_partial_export(self.h, C.c_uint64(nbytes), buf))
+        return buf.raw
+
+    def partial_import(self, handle: bytes):
+        buf = C.create_string_buffer(handle, 64)
+        self._check(self.lib.rl_partial_import(self.h, buf))
+
     def queue_reset(self, stream: int = 0):
         self._check(self.lib.rl_queue_reset(self.h, C.c_void_p(stream)))
 

@@ -64,7 +64,9 @@ struct rl_ctx {
     // work buffers
     DevBuf counters, queue, jobs, prefix, frame, partial, rays, hits;
     // cross-GPU queue (CUDA IPC): the owner allocates it, peers map it
-    DevBuf shared_queue_own;
+    DevBuf shared_queue_own, shared_partial_own;
+    float* shared_partial = nullptr;
+    bool shared_partial_imported = false;
     unsigned long long* shared_queue = nullptr;
     bool shared_queue_imported = false;
 };
@@ -149,6 +151,8 @@ void rl_destroy(rl_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->shared_queue_imported && c->shared_queue) cudaIpcCloseMemHandle(c->shared_queue);
+    if (c->shared_partial_imported && c->shared_partial) cudaIpcCloseMemHandle(c->shared_partial);
+    c->shared_partial_own.release();
     c->shared_queue_own.release();
     DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
                      &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->bvh_aabb,
@@ -569,6 +573,31 @@ int rl_queue_import(rl_ctx* c, const void* handle64) {
     return RL_OK;
 }
 
+int rl_partial_export(rl_ctx* c, uint64_t bytes, void* handle64) {
+    if (!c || !handle64 || bytes == 0) return RL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->shared_partial_own.reserve(bytes));
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, c->shared_partial_own.p));
+    memcpy(handle64, &h, sizeof(h));
+    c->shared_partial = c->shared_partial_own.as<float>();
+    c->shared_partial_imported = false;
+    return RL_OK;
+}
+
+int rl_partial_import(rl_ctx* c, const void* handle64) {
+    if (!c || !handle64) return RL_E_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (c->shared_partial_imported && c->shared_partial) cudaIpcCloseMemHandle(c->shared_partial);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->shared_partial = (float*)p;
+    c->shared_partial_imported = true;
+    return RL_OK;
+}
+
 int rl_queue_reset(rl_ctx* c, void* stream) {
     if (!c) return RL_E_INVALID;
     if (!c->shared_queue || c->shared_queue_imported) return fail(c, RL_E_INVALID, "only the exporting ctx resets the shared queue");
@@ -580,7 +609,9 @@ int rl_queue_reset(rl_ctx* c, void* stream) {
 
 int rl_render_ow_shared(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs, int32_t n_jobs,
                         void* d_partial, void* stream) {
-    if (!c || !cam || !d_partial) return RL_E_INVALID;
+    if (!c || !cam) return RL_E_INVALID;
+    if (!d_partial) d_partial = c->shared_partial;  // fused gather: store straight into the owner's buffer
+    if (!d_partial) return fail(c, RL_E_INVALID, "no partial buffer: pass one or call rl_partial_export / rl_partial_import");
     if (!c->has_scene || c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_NO_SCENE, "no OW scene uploaded");
     if (!c->shared_queue) return fail(c, RL_E_INVALID, "no shared queue: call rl_queue_export / rl_queue_import first");
     if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0) || cam->max_depth < 0)
@@ -597,6 +628,7 @@ int rl_render_ow_shared(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
 }
 
 int rl_ow_reduce_device(rl_ctx* c, const rl_ow_camera* cam, const void* d_partial, void* d_out, void* stream) {
+    if (c && !d_partial) d_partial = c->shared_partial;
     if (!c || !cam || !d_partial || !d_out) return RL_E_INVALID;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;

@@ -349,7 +349,7 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
 
 template <bool COUNT, int TRAV, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
-                                                   unsigned long long* __restrict__ queue, Counters* counters, int sys_queue) {
+                                                   unsigned long long* __restrict__ queue, Counters* counters, int sys_queue, int qbatch) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
     const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
@@ -359,6 +359,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
     float3 acc = f3(0.0f, 0.0f, 0.0f);
     Path p;
     p.depth = 0;
+    // warp-uniform queue state: the current reserved batch and the prefetched next one
+    long long cur_next = 0, cur_end = 0;
+    bool q_dry = false;
+    unsigned long long next_base = 0;
+    if (lane == 0) next_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
+                                         : atomicAdd(queue, (unsigned long long)qbatch);
     while (true) {
         // ---- retire finished items, refill idle lanes (warp-aggregated queue pop) ----
         if (has_item && !alive && s == s_end) {
@@ -371,21 +377,27 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
         bool need = !has_item && !done;
         unsigned mask = __ballot_sync(0xffffffffu, need);
         if (mask) {
-            int leader = __ffs(mask) - 1;
-            unsigned long long base = 0;
-            if (lane == (unsigned)leader) {
-                // sys_queue: ONE counter in rank 0's HBM shared by every GPU of the box (CUDA IPC mapping, popped
-                // over NVLink) — a dynamic tile queue at warp granularity with no host in the loop
-                base = sys_queue ? atomicAdd_system(queue, (unsigned long long)__popc(mask))
-                                 : atomicAdd(queue, (unsigned long long)__popc(mask));
+            // The warp owns a reserved batch [cur_next, cur_end) and a PREFETCHED next batch whose atomic was issued
+            // one batch ago, so the round trip to the counter (one ONE counter in rank 0's HBM when sys_queue is
+            // set: CUDA IPC mapping popped over NVLink — a dynamic tile queue with no host in the loop) overlaps
+            // rendering instead of stalling the warp at every pop.
+            if (cur_next >= cur_end && !q_dry) {
+                unsigned long long base = __shfl_sync(0xffffffffu, next_base, 0);
+                cur_next = (long long)base;
+                cur_end = cur_next + qbatch < jt.n_items ? cur_next + qbatch : jt.n_items;
+                if (cur_next >= jt.n_items) {
+                    q_dry = true;
+                    cur_end = cur_next;
+                } else if (lane == 0) {
+                    next_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
+                                          : atomicAdd(queue, (unsigned long long)qbatch);
+                }
             }
-            base = __shfl_sync(0xffffffffu, base, leader);
+            long long avail = cur_end - cur_next;
+            int rank_in = __popc(mask & ((1u << lane) - 1u));
             if (need) {
-                long long item = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
-                // items whose padded pixel falls outside the rectangle are skipped by taking the next round
-                if (item >= jt.n_items) {
-                    done = true;
-                } else {
+                if (rank_in < avail) {
+                    long long item = cur_next + rank_in;
                     int j = find_job(jt, item);
                     rl_job job = jt_job(jt, j);
                     long long local = item - jt_prefix(jt, j);
@@ -394,7 +406,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
                     int ck = (int)(local / pp);
                     int px, py;
                     tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
-                    if (px < w && py < hgt) {
+                    if (px < w && py < hgt) {  // padded slots outside the rectangle are simply skipped
                         x = job.x0 + px;
                         y = job.y0 + py;
                         chunk = job.chunk_begin + ck;
@@ -402,8 +414,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
                         acc = f3(0.0f, 0.0f, 0.0f);
                         has_item = true;
                     }
+                } else if (q_dry) {
+                    done = true;
                 }
             }
+            int taken = __popc(mask);
+            cur_next += taken < avail ? taken : avail;
         }
         if (__all_sync(0xffffffffu, done && !has_item)) break;
         // ---- path regeneration ----
@@ -723,7 +739,7 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     static const int variant = env_int("RL_OW_KERNEL_V", 3);
     static const int svc_num = env_int("RL_OW_SVC", 8), leaf_num = env_int("RL_OW_LEAF", 12);
     int per_sm = 0;
-    typedef void (*K1)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int);
+    typedef void (*K1)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
     K1 k1 = nullptr;
     static const int minb = env_int("RL_OW_MINB", 4);
     if (variant == 1) k1 = instrumented ? (K1)k_ow_render<true, 0, 2> : (K1)k_ow_render<false, 0, 2>;
@@ -745,7 +761,10 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     if (grid > want && !shared_queue) grid = want;
     if (grid < 1) grid = 1;
     if (k1) {
-        k1<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq);
+        // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
+        long long per_warp = jt.n_items / (grid * 8 * 4);
+        int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
+        k1<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch);
     } else {
         if (instrumented)
             k_ow_render2<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num, sysq);

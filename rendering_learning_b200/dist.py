@@ -112,18 +112,40 @@ def render_ow_distributed(ctx, cam, first_sample: int, jobs: Sequence[Job], part
     return mine
 
 
-def setup_shared_queue(ctx) -> bool:
-    """Map rank 0's work counter into every rank (CUDA IPC).  Returns False when there is a single rank."""
+def setup_shared_queue(ctx, partial_bytes: int = 0) -> bool:
+    """Map rank 0's work counter (and, with partial_bytes > 0, its partial-sum buffer) into every rank with
+    CUDA IPC.  Returns False when there is a single rank."""
     import torch.distributed as dist
     rank, world = _rank_world()
     if world == 1:
         return False
-    box = [ctx.queue_export() if rank == 0 else None]
+    box = [None, None]
+    if rank == 0:
+        box = [ctx.queue_export(), ctx.partial_export(partial_bytes) if partial_bytes else None]
     dist.broadcast_object_list(box, src=0)
     if rank != 0:
         ctx.queue_import(box[0])
+        if box[1] is not None:
+            ctx.partial_import(box[1])
     dist.barrier()
     return True
+
+
+def render_ow_fused(ctx, cam, first_sample: int, out, n_chunks: int, height: int, width: int):
+    """OW render, fully device-driven: every GPU's persistent warps pop items from rank 0's counter and store
+    the finished partial sums straight into rank 0's buffer, both over NVLink peer memory.  The only
+    collectives are two 4-byte NCCL all-reduces used as stream-ordered rendezvous."""
+    import torch.distributed as dist
+    rank, world = _rank_world()
+    stream = current_stream_handle()
+    tok = _token(out.device)
+    if rank == 0:
+        ctx.queue_reset(stream)
+    dist.all_reduce(tok)  # no rank pops before the reset
+    ctx.render_ow_shared(cam, first_sample, [(0, 0, width, height, 0, n_chunks)], 0, stream)
+    dist.all_reduce(tok)  # every rank's stores have landed
+    if rank == 0:
+        ctx.ow_reduce_device(cam, 0, out.data_ptr(), stream)
 
 
 def render_ow_shared_queue(ctx, cam, first_sample: int, partial, out, n_chunks: int, height: int, width: int):
