@@ -371,7 +371,10 @@ struct Flattener {
                     lo[k] = std::fmin(a, b) - ar;
                     hi[k] = std::fmax(a, b) + ar;
                 }
-                push_aabb(fs, lo, hi, make_ref(REF_SPHERE, idx), id);
+                if (ar >= (double)OW_BIG_RADIUS && (int)fs->big_refs.size() < OW_MAX_BIG)
+                    fs->big_refs.push_back(make_ref(REF_SPHERE, idx));  // tested once per ray, outside the LBVH
+                else
+                    push_aabb(fs, lo, hi, make_ref(REF_SPHERE, idx), id);
                 return true;
             }
             case RL_OW_QUAD: {

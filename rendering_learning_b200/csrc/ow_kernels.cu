@@ -21,8 +21,6 @@
 namespace rl {
 namespace {
 
-constexpr float OW_BIG_RADIUS = 64.0f;  // spheres at least this large take the f64 quadratic
-
 struct OwCam {
     int width, height, spp, max_depth;
     int first_sample, n_chunks, defocus, pad;
@@ -84,12 +82,17 @@ struct OwHit {
 
 // One primitive test of world.hit: updates `h` when the primitive is hit closer than h.t.
 // `self_ref` is the primitive the ray starts on (never re-hit at t ~ 0; a sphere only at its far root).
-template <bool COUNT>
+// PRIMS: which primitive kinds the scene holds (bit 0 spheres, bit 1 triangles, bit 2 quads).  The render kernel is
+// instantiated for "spheres only" and "everything", so a sphere scene carries no triangle / quad / image code (smaller
+// code, fewer registers, fewer instruction-cache misses: ncu showed 8 % of issue slots lost to `no_instruction`).
+constexpr int PRIMS_SPHERES = 1, PRIMS_TRIS = 2, PRIMS_QUADS = 4, PRIMS_ALL = 7;
+
+template <bool COUNT, int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
                                              int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc) {
     const float3 o = pre.o, d = pre.d;
     int type = ref_type(ref), idx = ref_index(ref);
-    if (type == REF_SPHERE) {  // sphere.rs:34-75
+    if (PRIMS == PRIMS_SPHERES || type == REF_SPHERE) {  // sphere.rs:34-75
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
         if (COUNT) lc.prims++;
         float3 center = fma3(f3(dc), time, f3(c));
@@ -135,7 +138,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             return;
         }
         return;
-    } else if (type == REF_TRI) {  // flat/triangle.rs:60-95 (watertight test instead of the plane basis)
+    } else if ((PRIMS & PRIMS_TRIS) && type == REF_TRI) {  // flat/triangle.rs:60-95 (watertight test instead of the plane basis)
         if (ref == self_ref) return;
         float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
         if (COUNT) lc.tris++;
@@ -148,7 +151,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             return;
         }
         return;
-    } else {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
+    } else if (PRIMS & PRIMS_QUADS) {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
         if (ref == self_ref) return;
         const OwQuad& qd = sc.quads[idx];
         float4 n4 = qd.n, q4 = qd.q;
@@ -170,6 +173,21 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
     }
 }
 
+// same test from (o, d) alone: the v4 kernel does not keep the watertight shear constants live across its service
+// rounds; they are rebuilt at the triangle tests (0.5 per ray on the Cornell box, none on the cover scene)
+template <bool COUNT, int PRIMS>
+__device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, float3 o, float3 d, float time, int self_ref,
+                                                float tmin, OwHit& h, LocalCount<COUNT>& lc) {
+    RayPre pre;
+    if ((PRIMS & PRIMS_TRIS) && ref_type(ref) == REF_TRI) {
+        pre = make_pre(o, d);
+    } else {
+        pre.o = o;
+        pre.d = d;
+    }
+    ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, dot(d, d), time, self_ref, tmin, h, lc);
+}
+
 // world.hit(r, [tmin, inf)) through the LBVH (callback form; used by rl_trace_batch and the v1 kernel).
 template <bool COUNT, int TRAV = 0>
 __device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3 d, float time, int self_ref, float tmin,
@@ -187,15 +205,16 @@ __device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3
         ow_leaf_test<COUNT>(sc, ref, pre, a_dd, time, self_ref, tmin, *hp, lcr);
         return hp->t;
     };
-    if (TRAV == 1) bvh_traverse_ww<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, RL_INF, lc, leaf);
-    else bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, RL_INF, lc, leaf);
+    for (int k = 0; k < sc.n_big; k++) leaf(sc.big_refs[k], h.t);  // OW_BIG_RADIUS spheres live outside the LBVH
+    if (TRAV == 1) bvh_traverse_ww<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, h.t, lc, leaf);
+    else bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, h.t, lc, leaf);
     return h;
 }
 
 // state of one path (per lane)
 struct Path {
     float3 o, d;
-    float3 thr, rad;
+    float3 thr;
     float time;
     int depth;
     int self_ref;
@@ -206,32 +225,37 @@ __device__ __forceinline__ float ow_tmin(const Path& p) {
     return fmaf(1e-5f, max_abs(p.o), 1e-6f) * rsqrtf(dot(p.d, p.d));
 }
 
-template <bool COUNT>
+template <bool COUNT, int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, Path& p, const OwHit& h, uint4 rnd,
-                                         LocalCount<COUNT>& lc);
+                                         float3& rad, LocalCount<COUNT>& lc);
 
 template <bool COUNT, int TRAV>
-__device__ __forceinline__ bool ow_bounce(const DevScene& sc, const OwCam& cam, Path& p, uint4 rnd, LocalCount<COUNT>& lc) {
+__device__ __forceinline__ bool ow_bounce(const DevScene& sc, const OwCam& cam, Path& p, uint4 rnd, float3& rad,
+                                          LocalCount<COUNT>& lc) {
     OwHit h = ow_closest<COUNT, TRAV>(sc, p.o, p.d, p.time, p.self_ref, ow_tmin(p), lc);
-    return ow_shade<COUNT>(sc, cam, p, h, rnd, lc);
+    return ow_shade<COUNT>(sc, cam, p, h, rnd, rad, lc);
 }
 
-// hit record + emitted + scatter for the closest hit `h` of path `p` (camera.rs:246-258)
-template <bool COUNT>
+// hit record + emitted + scatter for the closest hit `h` of path `p` (camera.rs:246-258).  Returns false when the path
+// ends; `rad` is then the sample's colour.  (Only terminal events add radiance — a miss adds the background, a
+// DiffuseLight emits and never scatters, every scattering material emits black — so the reference's
+// `emitted + attenuation * ray_color(..)` recursion collapses to throughput x the single terminal term.)
+template <bool COUNT, int PRIMS>
 __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, Path& p, const OwHit& h, uint4 rnd,
-                                         LocalCount<COUNT>& lc) {
+                                         float3& rad, LocalCount<COUNT>& lc) {
+    rad = f3(0.0f, 0.0f, 0.0f);
     if (h.ref < 0) {  // camera.rs:256-258
-        p.rad = p.rad + p.thr * cam.background;
+        rad = p.thr * cam.background;
         return false;
     }
     if (COUNT) lc.shades++;
     int type = ref_type(h.ref), idx = ref_index(h.ref);
-    float3 pos, normal;
+    float3 pos = p.o, normal;
     float u = h.b1, v = h.b2;
-    int mat_id;
+    int mat_id = 0;
     bool uv_from_sphere = false;
     float3 outward = f3(0.0f, 1.0f, 0.0f);
-    if (type == REF_SPHERE) {
+    if (PRIMS == PRIMS_SPHERES || type == REF_SPHERE) {
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
         float3 center = fma3(f3(dc), p.time, f3(c));
         float3 q = fma3(p.d, h.t, p.o) - center;
@@ -239,7 +263,7 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
         pos = fma3(normalize_precise(q), fabsf(c.w), center);           // snapped back onto the surface
         mat_id = __float_as_int(dc.w);
         uv_from_sphere = true;
-    } else if (type == REF_TRI) {
+    } else if ((PRIMS & PRIMS_TRIS) && type == REF_TRI) {
         float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
         float b0 = 1.0f - h.b1 - h.b2;
         pos = f3(p0) * b0 + f3(p1) * h.b1 + f3(p2) * h.b2;
@@ -253,7 +277,7 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
             v = s1.w * b0 + s3.x * h.b1 + s3.z * h.b2;
         }
         mat_id = __float_as_int(p0.w);
-    } else {
+    } else if (PRIMS & PRIMS_QUADS) {
         const OwQuad& qd = sc.quads[idx];
         outward = f3(qd.n);
         float3 ip = fma3(p.d, h.t, p.o);
@@ -265,25 +289,28 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
     const DevMaterial m = sc.materials[mat_id];
     int kind = __float_as_int(m.b.w);
     int tex = __float_as_int(m.color.w);
-    if (uv_from_sphere && tex >= 0) {  // get_sphere_uv (sphere.rs:91-99); only image textures read it
+    if (uv_from_sphere && tex >= 0 && sc.n_images > 0) {  // get_sphere_uv (sphere.rs:91-99); only image textures read it
         float theta = acosf(fminf(fmaxf(-outward.y, -1.0f), 1.0f));
         float phi = atan2f(-outward.z, outward.x) + 3.14159265358979f;
         u = phi * (1.0f / 6.28318530717959f);
         v = theta * (1.0f / 3.14159265358979f);
     }
     if (kind == RL_MAT_OW_DIFFUSE_LIGHT) {  // material.rs:178-195
-        p.rad = p.rad + p.thr * tex_value(sc, tex, u, v, pos);
+        rad = p.thr * tex_value(sc, tex, u, v, pos);
         return false;
     }
     float3 dir;
     float3 atten;
+    // Lambertian and Metal both draw a UnitSphere sample (Metal even with fuzz = 0, material.rs:113): evaluated once,
+    // before the material branches, so the warp runs it converged
+    const float3 uvec = kind == RL_MAT_OW_DIELECTRIC ? f3(0.0f, 0.0f, 0.0f) : unit_vector(u01(rnd.x), u01(rnd.y));
     if (kind == RL_MAT_OW_LAMBERTIAN) {  // material.rs:74-92
-        dir = normal + unit_vector(u01(rnd.x), u01(rnd.y));
+        dir = normal + uvec;
         if (fabsf(dir.x) <= 1e-8f && fabsf(dir.y) <= 1e-8f && fabsf(dir.z) <= 1e-8f) dir = normal;
         atten = tex_value(sc, tex, u, v, pos);
     } else if (kind == RL_MAT_OW_METAL) {  // material.rs:105-122
         float3 refl = p.d - normal * (2.0f * dot(p.d, normal));
-        dir = fma3(unit_vector(u01(rnd.x), u01(rnd.y)), m.a.x, normalize(refl));
+        dir = fma3(uvec, m.a.x, normalize(refl));
         if (!(dot(dir, normal) > 0.0f)) return false;
         atten = f3(m.color);
     } else {  // Dielectric, material.rs:139-176
@@ -342,7 +369,6 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
     p.d = sample_p - origin;
     p.time = u01(r.z);
     p.thr = f3(1.0f, 1.0f, 1.0f);
-    p.rad = f3(0.0f, 0.0f, 0.0f);
     p.depth = cam.max_depth;
     p.self_ref = -1;
 }
@@ -436,9 +462,10 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
             unsigned pixel = (unsigned)(y * cam.width + x);
             unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
             uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
-            bool cont = ow_bounce<COUNT, TRAV>(sc, cam, p, rnd, lc);
+            float3 rad;
+            bool cont = ow_bounce<COUNT, TRAV>(sc, cam, p, rnd, rad, lc);
             if (!cont) {
-                acc = acc + p.rad;  // samples are folded in order (camera.rs:174)
+                acc = acc + rad;  // samples are folded in order (camera.rs:174)
                 alive = false;
                 s++;
             }
@@ -447,182 +474,212 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
     lc.flush(counters);
 }
 
-// ---- v2: warp-scheduled state machine -----------------------------------------------------------------------
-// ncu on v1 (profiles/r01_ncu_k_ow_render_v1.json) shows 11 of 32 lanes active per issued instruction: every
-// lane runs its own traversal loop, leaf tests sit inside that loop, and a bounce ends only when the slowest
-// lane of the warp is done.  v2 keeps the per-lane persistent paths but lets the WARP choose, every iteration,
-// one of three actions from ballots of the lane states:
-//     inner step : lanes at an inner BVH node visit it (two slab tests, push / pop)
-//     leaf step  : lanes parked at a leaf run the primitive test           (postponed until enough lanes wait)
-//     service    : lanes whose traversal finished shade + scatter, dead paths are regenerated, finished items
-//                  retired and refilled from the queue                       (postponed until enough lanes wait)
-// so each action runs with a popc-checked minimum number of active lanes instead of whatever divergence leaves.
-constexpr int TRAV_DONE = (int)0x80000000;
-enum { PH_NEED = 0, PH_TRAV = 1, PH_SHADE = 2, PH_IDLE = 3 };
-
-template <bool COUNT>
-__global__ void __launch_bounds__(256, 2) k_ow_render2(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
-                                                       unsigned long long* __restrict__ queue, Counters* counters,
-                                                       int svc_num, int leaf_num, int sys_queue) {
+// ---- v4: resumable traversal + threshold-triggered service ---------------------------------------------------------
+// ncu on v3 (profiles/r01_ncu_k_ow_render_v3.json, r01_ncu_ow_c5.json): 10.8 of 32 lanes per issued instruction on the
+// cover scene and 6.3 on the Cornell box — a bounce (traversal + shade) ends only when the slowest lane's traversal
+// does.  Here the traversal state of a lane (node, stack, hit) survives across "service" rounds: the warp leaves the
+// traversal loop as soon as `svc_min` lanes wait for service (shade + scatter, retire, refill, regenerate), services
+// exactly those lanes, and drops back into the loop where the other lanes simply resume (Aila & Laine 2009's
+// persistent while-while with dynamic fetch, with the fetch replaced by a full material evaluation).  The v2 state
+// machine tried the same with one ballot-scheduled action per single step and lost to its own scheduling overhead;
+// this version keeps v3's tight inner loops and pays two ballots per leaf round.  Per-lane arithmetic is unchanged,
+// so the image is bit-identical to v3's.
+//
+// v5: the while-while loop still wastes lanes at SEGMENT level — every leaf round waits for the lane with the longest
+// run of inner nodes (mean ~5, max over 32 lanes ~20 on the cover scene, which is the measured 10-12 of 32 lanes).  So
+// every iteration is ONE node step for every lane at an inner node; lanes that reach a leaf park, and the leaf test
+// runs for all parked lanes together once `leaf_min` of them wait (or nobody can step).  leaf_min = 32 degenerates to
+// the while-while schedule (v4).  ncu (profiles/r01_ncu_k_ow_render_v4_v5.json): node steps run at 20 instead of 12.5
+// lanes, the whole kernel at 16 instead of 11.3.
+template <bool COUNT, int MINB, int PRIMS>
+__global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
+                                                          unsigned long long* __restrict__ queue, Counters* counters,
+                                                          int sys_queue, int qbatch, int svc_min, int leaf_min) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
-    // item
-    bool has_item = false, queue_empty = false;
-    int x = 0, y = 0, chunk = 0, s = 0, s_end = 0;
-    float3 acc = f3(0.0f, 0.0f, 0.0f);
+    // item.  Cold per-lane state (touched once per path or once per item, never inside the traversal loop) lives in
+    // shared memory, [word][thread] so every access is conflict free; that is ~10 registers the traversal loop gets
+    // back (ptxas: the 64-register build spilled 262 B with them in registers).
+    __shared__ float sm_acc[3][256], sm_thr[3][256];
+    __shared__ int sm_x[256], sm_y[256], sm_chunk[256], sm_send[256];
+    const int tid = threadIdx.x;
+    bool has_item = false, alive = false, done = false;
+    int s = 0;
+    unsigned pixel = 0;
     // path
     Path p;
     p.depth = 0;
-    // traversal
-    RayPre pre = make_pre(f3(0.0f, 0.0f, 0.0f), f3(0.0f, 0.0f, 1.0f));
-    float a_dd = 1.0f, tmin = 0.0f;
+    // traversal (resumable)
+    int node = TRAV_END, sp = 0;
+    int stack_node[BVH_STACK];
+    float3 inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
+    float tmin = 0.0f;
     OwHit hit;
     hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
-    int node = TRAV_DONE, sp = 0;
-    int stack_node[BVH_STACK];
-    float stack_t[BVH_STACK];
-    int phase = PH_NEED;
-
-    auto start_traversal = [&]() {
-        pre = make_pre(p.o, p.d);
-        a_dd = dot(p.d, p.d);
-        tmin = ow_tmin(p);
-        hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
-        sp = 0;
-        node = sc.n_bvh_prims > 0 ? 0 : TRAV_DONE;
-        phase = node == TRAV_DONE ? PH_SHADE : PH_TRAV;
-        if (COUNT) lc.rays++;
-    };
-    auto pop = [&]() {
-        node = TRAV_DONE;
-        while (sp > 0) {
-            sp--;
-            if (stack_t[sp] <= slack(hit.t)) { node = stack_node[sp]; break; }
-        }
-        if (node == TRAV_DONE) phase = PH_SHADE;
-    };
-
+    // queue (warp-uniform, one slot per warp in shared memory): the current reserved batch [next, end) and the base of
+    // the prefetched next batch, whose atomic was issued one batch ago
+    __shared__ long long sm_qnext[8], sm_qend[8];
+    __shared__ unsigned long long sm_qbase[8];
+    __shared__ int sm_qdry[8];
+    const int wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        sm_qnext[wid] = sm_qend[wid] = 0;
+        sm_qdry[wid] = 0;
+        sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
+                                  : atomicAdd(queue, (unsigned long long)qbatch);
+    }
+    __syncwarp();
     while (true) {
-        const bool trav = phase == PH_TRAV;
-        const unsigned m_inner = __ballot_sync(0xffffffffu, trav && node >= 0);
-        const unsigned m_leaf = __ballot_sync(0xffffffffu, trav && node < 0);
-        const unsigned m_wait = __ballot_sync(0xffffffffu, phase == PH_NEED || phase == PH_SHADE);
-        if ((m_inner | m_leaf | m_wait) == 0u) break;
-        const int n_inner = __popc(m_inner), n_leaf = __popc(m_leaf), n_wait = __popc(m_wait);
-        const int n_trav = n_inner + n_leaf;
-        if (n_trav == 0 || n_wait >= max(1, ((n_trav + n_wait) * svc_num) >> 5)) {
-            // ---------------- service: shade, retire, refill, regenerate ----------------
-            if (phase == PH_SHADE) {
-                unsigned pixel = (unsigned)(y * cam.width + x);
-                unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
-                uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
-                if (ow_shade<COUNT>(sc, cam, p, hit, rnd, lc)) {
-                    start_traversal();
-                } else {
-                    acc = acc + p.rad;  // samples are folded in order (camera.rs:174)
-                    s++;
-                    phase = PH_NEED;
-                }
-            }
-            if (phase == PH_NEED && has_item && s == s_end) {
-                size_t idx = (((size_t)chunk * cam.height + y) * cam.width + x) * 3;
-                partial[idx + 0] = acc.x;
-                partial[idx + 1] = acc.y;
-                partial[idx + 2] = acc.z;
-                has_item = false;
-            }
-            const bool need = phase == PH_NEED && !has_item && !queue_empty;
-            const unsigned mask = __ballot_sync(0xffffffffu, need);
-            if (mask) {  // one warp-aggregated pop for all requesting lanes
-                int leader = __ffs(mask) - 1;
-                unsigned long long base = 0;
-                if (lane == (unsigned)leader) {
-                // sys_queue: ONE counter in rank 0's HBM shared by every GPU of the box (CUDA IPC mapping, popped
-                // over NVLink) — a dynamic tile queue at warp granularity with no host in the loop
-                base = sys_queue ? atomicAdd_system(queue, (unsigned long long)__popc(mask))
-                                 : atomicAdd(queue, (unsigned long long)__popc(mask));
-            }
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (need) {
-                    long long item = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
-                    if (item >= jt.n_items) {
-                        queue_empty = true;
-                    } else {
-                        int j = find_job(jt, item);
-                        rl_job job = jt_job(jt, j);
-                        long long local = item - jt_prefix(jt, j);
-                        int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
-                        long long pp = padded_pixels(w, hgt);
-                        int ck = (int)(local / pp);
-                        int px, py;
-                        tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
-                        if (px < w && py < hgt) {
-                            x = job.x0 + px;
-                            y = job.y0 + py;
-                            chunk = job.chunk_begin + ck;
-                            chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
-                            if (cam.max_depth <= 0) s = s_end;  // depth 0: every sample is black
-                            acc = f3(0.0f, 0.0f, 0.0f);
-                            has_item = true;
-                        }
-                    }
-                }
-            }
-            if (phase == PH_NEED) {
-                if (has_item && s < s_end) {
-                    ow_camera_ray(cam, x, y, (unsigned)(cam.first_sample + s), p);
-                    start_traversal();
-                } else if (!has_item && queue_empty) {
-                    phase = PH_IDLE;
-                }
-            }
-        } else if (n_inner == 0 || n_leaf >= max(1, (n_trav * leaf_num) >> 5)) {
-            // ---------------- leaf step ----------------
-            if (trav && node < 0) {
-                ow_leaf_test<COUNT>(sc, ~node, pre, a_dd, p.time, p.self_ref, tmin, hit, lc);
-                pop();
-            }
-        } else {
-            // ---------------- inner step ----------------
-            if (trav && node >= 0) {
-                const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
-                float4 a = np[0], b = np[1], c = np[2];
-                int4 d = *reinterpret_cast<const int4*>(np + 3);
-                if (COUNT) lc.nodes++;
-                const float tmax = hit.t;
-                float t0x = (a.x - pre.o.x) * pre.inv_d.x, t1x = (a.w - pre.o.x) * pre.inv_d.x;
-                float t0y = (a.y - pre.o.y) * pre.inv_d.y, t1y = (b.x - pre.o.y) * pre.inv_d.y;
-                float t0z = (a.z - pre.o.z) * pre.inv_d.z, t1z = (b.y - pre.o.z) * pre.inv_d.z;
-                float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-                float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
-                float u0x = (b.z - pre.o.x) * pre.inv_d.x, u1x = (c.y - pre.o.x) * pre.inv_d.x;
-                float u0y = (b.w - pre.o.y) * pre.inv_d.y, u1y = (c.z - pre.o.y) * pre.inv_d.y;
-                float u0z = (c.x - pre.o.z) * pre.inv_d.z, u1z = (c.w - pre.o.z) * pre.inv_d.z;
-                float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));
-                float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));
-                bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
-                if (h0 && h1) {
-                    int nearc = d.x, farc = d.y;
-                    float tf = n1;
-                    if (n1 < n0) { nearc = d.y; farc = d.x; tf = n0; }
-                    if (sp < BVH_STACK) {
-                        stack_node[sp] = farc;
-                        stack_t[sp] = tf;
-                        sp++;
-                    } else {
-                        lc.overflow++;
-                    }
-                    node = nearc;
-                } else if (h0) {
-                    node = d.x;
-                } else if (h1) {
-                    node = d.y;
-                } else {
-                    pop();
-                }
+        // ================= service: every lane that is not mid-traversal =================
+        const bool svc = node == TRAV_END && !done;
+        if (svc && alive) {  // its traversal just finished: hit record + emitted + scatter
+            unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
+            uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
+            float3 rad;
+            p.thr = f3(sm_thr[0][tid], sm_thr[1][tid], sm_thr[2][tid]);
+            if (!ow_shade<COUNT, PRIMS>(sc, cam, p, hit, rnd, rad, lc)) {
+                sm_acc[0][tid] += rad.x;  // samples are folded in order (camera.rs:174)
+                sm_acc[1][tid] += rad.y;
+                sm_acc[2][tid] += rad.z;
+                alive = false;
+                s++;
+            } else {
+                sm_thr[0][tid] = p.thr.x;
+                sm_thr[1][tid] = p.thr.y;
+                sm_thr[2][tid] = p.thr.z;
             }
         }
+        if (svc && has_item && !alive && s == sm_send[tid]) {
+            size_t idx = (((size_t)sm_chunk[tid] * cam.height + sm_y[tid]) * cam.width + sm_x[tid]) * 3;
+            partial[idx + 0] = sm_acc[0][tid];
+            partial[idx + 1] = sm_acc[1][tid];
+            partial[idx + 2] = sm_acc[2][tid];
+            has_item = false;
+        }
+        const bool need = svc && !has_item;
+        const unsigned mask = __ballot_sync(FULL, need);
+        if (mask) {  // warp-aggregated pop from the reserved batch; the next batch's atomic is already in flight
+            long long cur_next = sm_qnext[wid], cur_end = sm_qend[wid];
+            bool q_dry = sm_qdry[wid] != 0;
+            __syncwarp();
+            if (cur_next >= cur_end && !q_dry) {
+                cur_next = (long long)sm_qbase[wid];
+                cur_end = cur_next + qbatch < jt.n_items ? cur_next + qbatch : jt.n_items;
+                __syncwarp();
+                if (cur_next >= jt.n_items) {
+                    q_dry = true;
+                    cur_end = cur_next;
+                } else if (lane == 0) {
+                    sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
+                                              : atomicAdd(queue, (unsigned long long)qbatch);
+                }
+            }
+            long long avail = cur_end - cur_next;
+            int rank_in = __popc(mask & ((1u << lane) - 1u));
+            if (need) {
+                if (rank_in < avail) {
+                    long long item = cur_next + rank_in;
+                    int j = find_job(jt, item);
+                    rl_job job = jt_job(jt, j);
+                    long long local = item - jt_prefix(jt, j);
+                    int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
+                    long long pp = padded_pixels(w, hgt);
+                    int ck = (int)(local / pp);
+                    int px, py;
+                    tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
+                    if (px < w && py < hgt) {  // padded slots outside the rectangle are simply skipped
+                        int x = job.x0 + px, y = job.y0 + py, chunk = job.chunk_begin + ck, s_end;
+                        chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                        if (cam.max_depth <= 0) s = s_end;  // depth 0: every sample is black (camera.rs:239-241)
+                        pixel = (unsigned)(y * cam.width + x);
+                        sm_x[tid] = x;
+                        sm_y[tid] = y;
+                        sm_chunk[tid] = chunk;
+                        sm_send[tid] = s_end;
+                        sm_acc[0][tid] = sm_acc[1][tid] = sm_acc[2][tid] = 0.0f;
+                        has_item = true;
+                    }
+                } else if (q_dry) {
+                    done = true;
+                }
+            }
+            int taken = __popc(mask);
+            cur_next += taken < avail ? taken : avail;
+            if (lane == 0) {
+                sm_qnext[wid] = cur_next;
+                sm_qend[wid] = cur_end;
+                sm_qdry[wid] = q_dry ? 1 : 0;
+            }
+            __syncwarp();
+        }
+        if (svc && has_item && !alive && s < sm_send[tid]) {  // path regeneration
+            ow_camera_ray(cam, sm_x[tid], sm_y[tid], (unsigned)(cam.first_sample + s), p);
+            sm_thr[0][tid] = sm_thr[1][tid] = sm_thr[2][tid] = 1.0f;
+            alive = true;
+        }
+        if (svc && alive) {  // start the traversal of the lane's new ray
+            inv_d = f3(1.0f / p.d.x, 1.0f / p.d.y, 1.0f / p.d.z);
+            oi = p.o * inv_d;
+            tmin = ow_tmin(p);
+            hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
+            sp = 0;
+            if (COUNT) lc.rays++;
+            for (int k = 0; k < sc.n_big; k++)  // OW_BIG_RADIUS spheres: once per ray, here, with the serviced lanes
+                ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, p.time, p.self_ref, tmin, hit, lc);
+            node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
+        }
+        const unsigned m_done = __ballot_sync(FULL, done);
+        if (m_done == FULL) break;
+        // ================= traversal: until svc_min lanes wait for service =================
+        const int n_done = __popc(m_done);
+#define RL_NODE_STEP()                                                                                              \
+    {                                                                                                               \
+        const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);                                        \
+        float4 a = np[0], b = np[1], c = np[2];                                                                     \
+        int4 d = *reinterpret_cast<const int4*>(np + 3);                                                            \
+        if (COUNT) lc.nodes++;                                                                                      \
+        const float tmax = hit.t;                                                                                   \
+        float t0x = fmaf(a.x, inv_d.x, -oi.x), t1x = fmaf(a.w, inv_d.x, -oi.x);                                     \
+        float t0y = fmaf(a.y, inv_d.y, -oi.y), t1y = fmaf(b.x, inv_d.y, -oi.y);                                     \
+        float t0z = fmaf(a.z, inv_d.z, -oi.z), t1z = fmaf(b.y, inv_d.z, -oi.z);                                     \
+        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));                    \
+        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));                    \
+        float u0x = fmaf(b.z, inv_d.x, -oi.x), u1x = fmaf(c.y, inv_d.x, -oi.x);                                     \
+        float u0y = fmaf(b.w, inv_d.y, -oi.y), u1y = fmaf(c.z, inv_d.y, -oi.y);                                     \
+        float u0z = fmaf(c.x, inv_d.z, -oi.z), u1z = fmaf(c.w, inv_d.z, -oi.z);                                     \
+        float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));                    \
+        float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));                    \
+        bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);                                                            \
+        int nearc = d.x, farc = d.y;                                                                                \
+        if (n1 < n0) { nearc = d.y; farc = d.x; }                                                                   \
+        if (h0 && h1) {                                                                                             \
+            if (sp < BVH_STACK) stack_node[sp++] = farc; else lc.overflow++;                                        \
+            node = nearc;                                                                                           \
+        } else if (h0 || h1) {                                                                                      \
+            node = h0 ? d.x : d.y;                                                                                  \
+        } else {                                                                                                    \
+            node = sp > 0 ? stack_node[--sp] : TRAV_END;                                                            \
+        }                                                                                                           \
+    }
+        while (true) {
+            // leaf round: every lane parked at a leaf tests it and pops
+            if (node < 0 && node != TRAV_END) {
+                ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, p.time, p.self_ref, tmin, hit, lc);
+                node = sp > 0 ? stack_node[--sp] : TRAV_END;
+            }
+            const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));
+            if (n_end == 32 || n_end - n_done >= svc_min) break;
+            // node steps, one per lane per iteration, until leaf_min lanes have parked (or ended) or none can step
+            const int keep = 32 - n_end - leaf_min;
+            int n_in;
+            do {
+                if (node >= 0) RL_NODE_STEP()
+                n_in = __popc(__ballot_sync(FULL, node >= 0));
+            } while (n_in > keep && n_in > 0);
+        }
+#undef RL_NODE_STEP
     }
     lc.flush(counters);
 }
@@ -733,44 +790,48 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     if (e != cudaSuccess) return e;
     const int sysq = shared_queue ? 1 : 0;
     // Kernel variants stay selectable for A/B profiling (DESIGN.md §"OW kernel variants", profiles/r01_ncu_k_ow_render_*):
-    //   RL_OW_KERNEL_V=1  per-lane if-if traversal loop                     (first version)
-    //   RL_OW_KERNEL_V=2  warp-scheduled state machine (ballot/popc picks inner / leaf / service steps)
-    //   RL_OW_KERNEL_V=3  while-while traversal, FMA slabs, cull-free pop   (default; RL_OW_MINB = blocks per SM)
-    static const int variant = env_int("RL_OW_KERNEL_V", 3);
-    static const int svc_num = env_int("RL_OW_SVC", 8), leaf_num = env_int("RL_OW_LEAF", 12);
-    int per_sm = 0;
-    typedef void (*K1)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
-    K1 k1 = nullptr;
-    static const int minb = env_int("RL_OW_MINB", 4);
-    if (variant == 1) k1 = instrumented ? (K1)k_ow_render<true, 0, 2> : (K1)k_ow_render<false, 0, 2>;
+    //   RL_OW_KERNEL_V=3  while-while traversal, FMA slabs, cull-free pop; a bounce ends with the warp's slowest lane
+    //   RL_OW_KERNEL_V=5  resumable traversal + threshold-triggered service, one node step per iteration with batched
+    //                     leaf tests (default); RL_OW_LEAF=32 degenerates to while-while inner loops ("v4")
+    //   RL_OW_MINB = resident CTAs per SM the kernel is compiled for (register budget), RL_OW_SVC = lanes that must
+    //   wait before the warp leaves the traversal loop to service them, RL_OW_LEAF = parked lanes per leaf round.
+    // (v1, the per-lane if-if loop, and v2, the one-action-per-step state machine, lost to v3 and were removed; their
+    //  ncu summaries stay under profiles/.)
+    static const int variant = env_int("RL_OW_KERNEL_V", 5);
+    static const int minb_env = env_int("RL_OW_MINB", 0);
+    static const int svc_min = env_int("RL_OW_SVC", 16), leaf_min = env_int("RL_OW_LEAF", 12);
+    static const int generic = env_int("RL_OW_GENERIC", 0);  // 1: never pick the spheres-only instantiation
+    typedef void (*K3)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
+    typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, int, int);
+    K3 k3 = nullptr;
+    K5 k4 = nullptr;
+    const bool spheres_only = !generic && sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0;
+    // measured (gpurun_out/sweep_ow4.log): the spheres-only build fits 64 registers (4 CTAs/SM) with 18 B of spills and
+    // wins there; the generic build is better at 80 registers (3 CTAs/SM)
+    const int minb = minb_env ? minb_env : (spheres_only ? 4 : 3);
     if (variant == 3) {
-        if (minb == 4) k1 = instrumented ? (K1)k_ow_render<true, 1, 4> : (K1)k_ow_render<false, 1, 4>;
-        else if (minb == 3) k1 = instrumented ? (K1)k_ow_render<true, 1, 3> : (K1)k_ow_render<false, 1, 3>;
-        else k1 = instrumented ? (K1)k_ow_render<true, 1, 2> : (K1)k_ow_render<false, 1, 2>;
-    }
-    if (k1) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, 256, 0);
+        k3 = instrumented ? (K3)k_ow_render<true, 1, 4> : (K3)k_ow_render<false, 1, 4>;
+    } else if (spheres_only) {
+        if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_SPHERES> : (K5)k_ow_render5<false, 4, PRIMS_SPHERES>;
+        else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_SPHERES> : (K5)k_ow_render5<false, 3, PRIMS_SPHERES>;
     } else {
-        if (instrumented) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render2<true>, 256, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ow_render2<false>, 256, 0);
+        if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_ALL> : (K5)k_ow_render5<false, 4, PRIMS_ALL>;
+        else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_ALL> : (K5)k_ow_render5<false, 3, PRIMS_ALL>;
     }
+    int per_sm = 0;
+    e = k3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, 256, 0)
+           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4, 256, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long want = (jt.n_items + 255) / 256;
-    long long grid = (long long)sm_count * per_sm;
+    long long grid = (long long)sm_count * per_sm;  // persistent: every SM full, a multiple of the SM count
     if (grid > want && !shared_queue) grid = want;
     if (grid < 1) grid = 1;
-    if (k1) {
-        // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
-        long long per_warp = jt.n_items / (grid * 8 * 4);
-        int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
-        k1<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch);
-    } else {
-        if (instrumented)
-            k_ow_render2<true><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num, sysq);
-        else
-            k_ow_render2<false><<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, svc_num, leaf_num, sysq);
-    }
+    // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
+    long long per_warp = jt.n_items / (grid * 8 * 4);
+    int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
+    if (k3) k3<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch);
+    else k4<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch, svc_min, leaf_min);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,12 @@ __host__ __device__ inline int make_ref(int type, int index) { return (type << 2
 __host__ __device__ inline int ref_type(int ref) { return (ref >> 28) & 7; }
 __host__ __device__ inline int ref_index(int ref) { return ref & 0x0FFFFFFF; }
 
+// OW spheres at least this large (the r = 1000 ground of the cover scene) stay OUT of the LBVH: their box would
+// cover the whole scene, so every ray tests them anyway.  They go on a short "big" list that is tested once per ray
+// before the traversal (which then starts with a finite tmax), with the quadratic evaluated in f64.
+constexpr float OW_BIG_RADIUS = 64.0f;
+constexpr int OW_MAX_BIG = 8;  // more than this and the rest go through the LBVH like any other sphere
+
 // RTC analytic primitive (unit shape + composed, pre-inverted transform). 176 B.
 struct RtcPrim {
     float4 inv[3];   // world -> object affine rows (inv_total = inv_leaf * ... * inv_root)
@@ -94,6 +100,7 @@ struct DevScene {
     int n_prims;      // RTC analytic prims (brute force)
     int n_tris, n_spheres, n_quads;
     int n_bvh_prims, n_bvh_nodes;  // traversal nodes (>= 1 when n_bvh_prims >= 1)
+    int n_big;                     // OW: leaf refs tested brute force before the traversal
     int n_materials, n_textures, n_lights, n_images, n_xforms;
     int has_transparency;
     int max_reflection_depth;
@@ -111,6 +118,7 @@ struct DevScene {
     const DevImage* images;
     const DevLight* lights;
     const BvhNode* nodes;
+    const int* big_refs;
 };
 
 // host-side result of flattening
@@ -132,6 +140,7 @@ struct FlatScene {
     std::vector<float> bvh_aabb;   // [n][6]
     std::vector<int> bvh_ref;      // [n]
     std::vector<int> bvh_node_id;  // [n]
+    std::vector<int> big_refs;     // OW leaf refs kept out of the LBVH (OW_BIG_RADIUS)
     int has_transparency = 0;
     int max_reflection_depth = 5;
     float void_color[3] = {0, 0, 0};
