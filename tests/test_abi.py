@@ -72,3 +72,59 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
                 assert "orc_" not in txt, f
+
+
+# ---- rust/rl-b200-sys (uncompilable here: no cargo/rustc) is kept in step with the header by parsing both ----
+_C2RUST = {"int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "uint32_t": "u32", "float": "f32", "double": "f64",
+           "int": "c_int", "void": "c_void", "char": "c_char"}
+
+
+def _c_structs():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef struct \w+ \{(.*?)\}\s*(\w+);", src, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.*)", decl)
+            const, ctype, ptr0, rest = m.groups()
+            for item in rest.split(","):
+                item = item.strip()
+                ptr = bool(ptr0) or item.startswith("*")
+                item = item.lstrip("* ")
+                am = re.match(r"(\w+)\[(\d+)\]", item)
+                base = _C2RUST.get(ctype, ctype)
+                if am:
+                    fields.append((am.group(1), f"[{base}; {am.group(2)}]"))
+                elif ptr:
+                    fields.append((item, ("*const " if const else "*mut ") + base))
+                else:
+                    fields.append((item, base))
+        out[name] = fields
+    return out
+
+
+def _rust_structs():
+    src = open(os.path.join(ROOT, "rust", "rl-b200-sys", "src", "lib.rs")).read()
+    out = {}
+    for name, body in re.findall(r"pub struct (\w+) \{(.*?)\n\}", src, flags=re.S):
+        out[name] = [(a, b.strip()) for a, b in re.findall(r"pub (\w+): ([^,\n]+),", body)]
+    return src, out
+
+
+def test_rust_sys_matches_header():
+    cs = _c_structs()
+    src, rs = _rust_structs()
+    for name, fields in cs.items():
+        assert name in rs, f"{name} missing from rl-b200-sys"
+        assert rs[name] == fields, (name, rs[name], fields)
+    m = re.search(r'extern "C" \{(.*?)\n\}', src, flags=re.S)
+    rust_fns = set(re.findall(r"pub fn (rl_\w+)\(", m.group(1)))
+    assert rust_fns == _declared(), rust_fns ^ _declared()
+    consts = dict(re.findall(r"pub const (RL_\w+): \w+ = (-?\d+);", src))
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for k, v in re.findall(r"\b(RL_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr):
+        assert consts.get(k) == v, (k, v, consts.get(k))
+    assert consts["RL_B200_ABI_VERSION"] == re.search(r"#define RL_B200_ABI_VERSION (\d+)", hdr).group(1)
