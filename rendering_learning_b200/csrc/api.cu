@@ -55,7 +55,7 @@ struct rl_ctx {
     DevBuf prims, tri_verts, tri_shade, xforms, spheres, quads, sphere_node, quad_node, materials, textures,
         images, lights, nodes;
     std::vector<DevBuf> image_texels;
-    DevBuf big_refs, bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
+    DevBuf big_refs, csg, bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
         node_aabb, lbvh_counters;
     DevScene ds{};
     rl_scene_info info{};
@@ -155,7 +155,7 @@ void rl_destroy(rl_ctx* c) {
     c->shared_partial_own.release();
     c->shared_queue_own.release();
     DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
-                     &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->bvh_aabb,
+                     &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
                      &c->jobs, &c->prefix, &c->frame, &c->partial, &c->rays, &c->hits};
@@ -242,6 +242,7 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     int n = (int)fs.bvh_ref.size();
     int nn = n >= 2 ? n - 1 : (n == 1 ? 1 : 0);
     CK(c, upload(c->big_refs, fs.big_refs, s));
+    CK(c, upload(c->csg, fs.csg, s));
     CK(c, upload(c->bvh_aabb, fs.bvh_aabb, s));
     CK(c, upload(c->bvh_ref, fs.bvh_ref, s));
     CK(c, upload(c->bvh_node_id, fs.bvh_node_id, s));
@@ -288,6 +289,7 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     d.n_bvh_prims = n;
     d.n_bvh_nodes = nn;
     d.n_big = (int)fs.big_refs.size();
+    d.n_csg = (int)fs.csg.size();
     d.n_materials = (int)fs.materials.size();
     d.n_textures = (int)fs.textures.size();
     d.n_lights = (int)fs.lights.size();
@@ -310,6 +312,7 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     d.lights = c->lights.as<DevLight>();
     d.nodes = c->nodes.as<BvhNode>();
     d.big_refs = c->big_refs.as<int>();
+    d.csg = c->csg.as<int4>();
 
     rl_scene_info& si = c->info;
     si = rl_scene_info{};

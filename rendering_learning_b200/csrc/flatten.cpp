@@ -123,6 +123,7 @@ struct Flattener {
     FlatScene* fs;
     std::string* err;
     int rc = RL_OK;
+    int csg_depth = 0;
 
     bool fail(int code, const std::string& msg) {
         if (rc == RL_OK) {
@@ -251,6 +252,7 @@ struct Flattener {
                 return true;
             }
             case RL_RTC_TRIANGLE: {
+                if (csg_depth > 0) return fail(RL_E_UNSUPPORTED, "triangles under a Csg are not lowered yet");
                 if (!check_material(nd.material)) return false;
                 const double* q = params(nd, 18);
                 if (!q) return false;
@@ -302,8 +304,31 @@ struct Flattener {
             }
             case RL_RTC_BOUNDED:
                 return rtc_node(nd.child_begin, fwd_total, inv_total, depth + 1);
-            case RL_RTC_CSG:
-                return fail(RL_E_UNSUPPORTED, "Csg objects are not lowered to the device yet (SURVEY.md §8f)");
+            case RL_RTC_CSG: {
+                // csg.rs:31-35.  Leaves are emitted in DFS order, so a CSG node's operands are the contiguous prim
+                // ranges [lo, mid) and [mid, hi); nodes are stored post-order (children before parents), which is the
+                // order the device filter applies them in (rtc_kernels.cu each_prim).
+                if (nd.flags < RL_CSG_UNION || nd.flags > RL_CSG_DIFFERENCE) return fail(RL_E_INVALID, "unknown CsgOperation");
+                const bool outermost = csg_depth == 0;
+                const int first = (int)fs->csg.size();
+                const int lo = (int)fs->prims.size();
+                csg_depth++;
+                bool ok = rtc_node(nd.child_begin, fwd_total, inv_total, depth + 1);
+                const int mid = (int)fs->prims.size();
+                ok = ok && rtc_node(nd.child_end, fwd_total, inv_total, depth + 1);
+                csg_depth--;
+                if (!ok) return false;
+                const int hi = (int)fs->prims.size();
+                fs->csg.push_back(make_int4(nd.flags, lo, mid, hi));
+                if (outermost) {
+                    const int count = (int)fs->csg.size() - first;
+                    for (int k = lo; k < hi; k++) {
+                        fs->prims[k].csg_first = first;
+                        fs->prims[k].csg_count = count;
+                    }
+                }
+                return true;
+            }
             default:
                 return fail(RL_E_INVALID, "unknown RTC node kind");
         }

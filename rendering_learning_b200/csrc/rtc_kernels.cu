@@ -213,12 +213,89 @@ struct RtcHit {
 };
 constexpr int NO_HIT = 0x7fffffff;
 
-template <bool COUNT>
+// CsgOperation::intersection_allowed (csg.rs:16-28)
+__device__ __forceinline__ bool csg_allowed(int op, bool left, bool in_left, bool in_right) {
+    if (op == RL_CSG_UNION) return left ? !in_right : !in_left;
+    if (op == RL_CSG_INTERSECTION) return left ? in_right : in_left;
+    return left ? !in_right : in_left;  // Difference
+}
+constexpr int CSG_CAP = 24;  // crossings one top-level Csg may produce along a ray (overflow is reported)
+
+template <bool COUNT, bool CSG>
 struct RtcTracer {
     const DevScene& sc;
     LocalCount<COUNT>& lc;
 
     __device__ __forceinline__ RtcTracer(const DevScene& s, LocalCount<COUNT>& l) : sc(s), lc(l) {}
+
+    // Calls f(i, prim, ts, n, tags) for every analytic primitive with the roots that reach the World's list, i.e.
+    // after every Csg above the leaf has filtered them (csg.rs:49-111); f returns true to stop.
+    //
+    // A top-level Csg owns a contiguous prim range.  Its leaves' crossings are gathered into a small per-thread
+    // list, stably sorted by t (gather order = leaf DFS order = the reference's "left list, then right list,
+    // sort_by t"), and the Csg nodes are applied bottom-up: each walks the surviving crossings of its range,
+    // toggling in_left / in_right exactly like filter_intersections (csg.rs:51-76).
+    template <class F>
+    __device__ __forceinline__ void each_prim(float3 o, float3 d, F f) {
+        int i = 0;
+        while (i < sc.n_prims) {
+            const RtcPrim& p = sc.prims[i];
+            if (!CSG || p.csg_count == 0) {
+                float3 lo = xf_point(p.inv, o), ld = xf_vec(p.inv, d);
+                float ts[4];
+                unsigned tags;
+                int n = prim_roots(p, lo, ld, ts, &tags);
+                if (COUNT) lc.prims++;
+                if (f(i, p, ts, n, tags)) return;
+                i++;
+                continue;
+            }
+            const int4 top = sc.csg[p.csg_first + p.csg_count - 1];
+            float ct[CSG_CAP];
+            int ci[CSG_CAP];  // prim << 8 | tag
+            int cn = 0;
+            for (int j = top.y; j < top.w; j++) {
+                const RtcPrim& q = sc.prims[j];
+                float3 lo = xf_point(q.inv, o), ld = xf_vec(q.inv, d);
+                float ts[4];
+                unsigned tags;
+                int n = prim_roots(q, lo, ld, ts, &tags);
+                if (COUNT) lc.prims++;
+                for (int k = 0; k < n; k++) {
+                    if (cn >= CSG_CAP) { lc.overflow++; break; }
+                    // stable insertion by t
+                    int e = cn++;
+                    while (e > 0 && ct[e - 1] > ts[k]) { ct[e] = ct[e - 1]; ci[e] = ci[e - 1]; e--; }
+                    ct[e] = ts[k];
+                    ci[e] = (j << 8) | (int)((tags >> (2 * k)) & 3u);
+                }
+            }
+            unsigned alive = cn >= 32 ? 0xffffffffu : ((1u << cn) - 1u);
+            for (int c = 0; c < p.csg_count; c++) {
+                const int4 nd = sc.csg[p.csg_first + c];
+                bool in_left = false, in_right = false;
+                for (int e = 0; e < cn; e++) {
+                    int j = ci[e] >> 8;
+                    if (!((alive >> e) & 1u) || j < nd.y || j >= nd.w) continue;
+                    bool left = j < nd.z;
+                    if (!csg_allowed(nd.x, left, in_left, in_right)) alive &= ~(1u << e);
+                    if (left) in_left = !in_left; else in_right = !in_right;
+                }
+            }
+            for (int j = top.y; j < top.w; j++) {
+                float ts[4];
+                unsigned tags = 0u;
+                int n = 0;
+                for (int e = 0; e < cn; e++)
+                    if (((alive >> e) & 1u) && (ci[e] >> 8) == j && n < 4) {
+                        tags |= (unsigned)(ci[e] & 3) << (2 * n);
+                        ts[n++] = ct[e];
+                    }
+                if (f(j, sc.prims[j], ts, n, tags)) return;
+            }
+            i = top.w;
+        }
+    }
 
     // closest hit per intersect::hit over World::intersect
     __device__ RtcHit closest(float3 o, float3 d) {
@@ -229,13 +306,7 @@ struct RtcTracer {
         h.node = -1;
         h.b1 = h.b2 = 0.0f;
         h.tag = 0;
-        for (int i = 0; i < sc.n_prims; i++) {
-            const RtcPrim& p = sc.prims[i];
-            float3 lo = xf_point(p.inv, o), ld = xf_vec(p.inv, d);
-            float ts[4];
-            unsigned tags;
-            int n = prim_roots(p, lo, ld, ts, &tags);
-            if (COUNT) lc.prims++;
+        each_prim(o, d, [&](int i, const RtcPrim& p, const float* ts, int n, unsigned tags) -> bool {
             for (int k = 0; k < n; k++) {
                 float t = ts[k];
                 if (t >= 0.0f && (t < h.t || (t == h.t && p.node >= h.node))) {
@@ -245,7 +316,8 @@ struct RtcTracer {
                     h.tag = (int)((tags >> (2 * k)) & 3u);
                 }
             }
-        }
+            return false;
+        });
         if (sc.n_bvh_prims > 0) {
             RayPre pre = make_pre(o, d);
             const TriVerts* tv = sc.tri_verts;
@@ -291,13 +363,7 @@ struct RtcTracer {
         float hit_last_t = -RL_INF;
         int hit_root = 0;
         float hit_ior = 1.0f;
-        for (int i = 0; i < sc.n_prims; i++) {
-            const RtcPrim& p = sc.prims[i];
-            float3 lo = xf_point(p.inv, o), ld = xf_vec(p.inv, d);
-            float ts[4];
-            unsigned tags;
-            int n = prim_roots(p, lo, ld, ts, &tags);
-            if (COUNT) lc.prims++;
+        each_prim(o, d, [&](int i, const RtcPrim& p, const float* ts, int n, unsigned) -> bool {
             float th = h.t;
             if (i == h.prim) {
                 // which root is the hit?  the one nearest to the recorded t (robust to re-evaluation)
@@ -331,7 +397,8 @@ struct RtcTracer {
                     any_other = true;
                 }
             }
-        }
+            return false;
+        });
         if (h.prim < 0) hit_ior = sc.materials[__float_as_int(sc.tri_verts[~h.prim].p0.w)].b.z;
         if (sc.n_bvh_prims > 0) {
             // every triangle is its own object with a single crossing (triangle.rs:63-101)
@@ -381,17 +448,13 @@ struct RtcTracer {
         if (COUNT) lc.rays++;
         if (!sc.has_transparency) {
             // every material is opaque: the first counted crossing already makes the product 0
-            for (int i = 0; i < sc.n_prims; i++) {
-                const RtcPrim& p = sc.prims[i];
-                float3 lo = xf_point(p.inv, point), ld = xf_vec(p.inv, d);
-                float ts[4];
-                unsigned tags;
-            int n = prim_roots(p, lo, ld, ts, &tags);
-                if (COUNT) lc.prims++;
-                for (int k = 0; k < n; k++)
-                    if (ts[k] > 0.0f && ts[k] < distance) return 0.0f;
-            }
             bool blocked = false;
+            each_prim(point, d, [&](int, const RtcPrim&, const float* ts, int n, unsigned) -> bool {
+                for (int k = 0; k < n; k++)
+                    if (ts[k] > 0.0f && ts[k] < distance) blocked = true;
+                return blocked;
+            });
+            if (blocked) return 0.0f;
             if (sc.n_bvh_prims > 0) {
                 RayPre pre = make_pre(point, d);
                 const TriVerts* tv = sc.tri_verts;
@@ -414,13 +477,7 @@ struct RtcTracer {
         // i.e. at the earliest SECOND in-range crossing of any analytic primitive (triangles cross once)
         float stop_t = RL_INF;
         int stop_node = 0x7fffffff;
-        for (int i = 0; i < sc.n_prims; i++) {
-            const RtcPrim& p = sc.prims[i];
-            float3 lo = xf_point(p.inv, point), ld = xf_vec(p.inv, d);
-            float ts[4];
-            unsigned tags;
-            int n = prim_roots(p, lo, ld, ts, &tags);
-            if (COUNT) lc.prims++;
+        each_prim(point, d, [&](int, const RtcPrim& p, const float* ts, int n, unsigned) -> bool {
             float first = RL_INF, second = RL_INF;
             for (int k = 0; k < n; k++) {
                 float t = ts[k];
@@ -433,21 +490,18 @@ struct RtcTracer {
                 stop_t = second;
                 stop_node = p.node;
             }
-        }
+            return false;
+        });
         // pass 2: product of transparency over first crossings that come before the stop
         float prod = 1.0f;
-        for (int i = 0; i < sc.n_prims; i++) {
-            const RtcPrim& p = sc.prims[i];
-            float3 lo = xf_point(p.inv, point), ld = xf_vec(p.inv, d);
-            float ts[4];
-            unsigned tags;
-            int n = prim_roots(p, lo, ld, ts, &tags);
+        each_prim(point, d, [&](int, const RtcPrim& p, const float* ts, int n, unsigned) -> bool {
             float first = RL_INF;
             for (int k = 0; k < n; k++)
                 if (ts[k] > 0.0f && ts[k] < distance) first = fminf(first, ts[k]);
             if (first < RL_INF && (first < stop_t || (first == stop_t && p.node <= stop_node)))
                 prod *= sc.materials[p.material].b.y;
-        }
+            return false;
+        });
         if (prod != 0.0f && sc.n_bvh_prims > 0) {
             RayPre pre = make_pre(point, d);
             const TriVerts* tv = sc.tri_verts;
@@ -628,7 +682,7 @@ __device__ __forceinline__ void camera_ray(const RtcCam& c, int px, int py, int 
 }
 
 // one thread per pixel; warps walk 8x4 pixel micro-tiles of each job rectangle
-template <bool COUNT>
+template <bool COUNT, bool CSG>
 __global__ void __launch_bounds__(128) k_rtc_render(DevScene sc, RtcCam cam, JobTable jt, float* __restrict__ out,
                                                     Counters* counters) {
     LocalCount<COUNT> lc;
@@ -641,7 +695,7 @@ __global__ void __launch_bounds__(128) k_rtc_render(DevScene sc, RtcCam cam, Job
         x += job.x0;
         y += job.y0;
         if (x < job.x1 && y < job.y1) {
-            RtcTracer<COUNT> tr(sc, lc);
+            RtcTracer<COUNT, CSG> tr(sc, lc);
             float3 acc = f3(0.0f, 0.0f, 0.0f);
             for (int nx = 0; nx < cam.aa; nx++)
                 for (int ny = 0; ny < cam.aa; ny++) {
@@ -659,14 +713,14 @@ __global__ void __launch_bounds__(128) k_rtc_render(DevScene sc, RtcCam cam, Job
     lc.flush(counters);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool CSG>
 __global__ void __launch_bounds__(128) k_rtc_trace(DevScene sc, const rl_ray* __restrict__ rays, unsigned long long n,
                                                    rl_hit* __restrict__ hits, Counters* counters) {
     LocalCount<COUNT> lc;
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         rl_ray r = rays[i];
-        RtcTracer<COUNT> tr(sc, lc);
+        RtcTracer<COUNT, CSG> tr(sc, lc);
         RtcHit h = tr.closest(f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.direction[0], r.direction[1], r.direction[2]));
         rl_hit o;
         o.node = h.prim == NO_HIT ? -1 : h.node;
@@ -700,8 +754,14 @@ cudaError_t launch_rtc_render(const DevScene& sc, const rl_rtc_camera* cam, cons
     c.aa = (int)aa;
     if (jt.n_items <= 0) return cudaSuccess;
     unsigned blocks = (unsigned)((jt.n_items + 127) / 128);
-    if (instrumented) k_rtc_render<true><<<blocks, 128, 0, stream>>>(sc, c, jt, d_out, d_counters);
-    else k_rtc_render<false><<<blocks, 128, 0, stream>>>(sc, c, jt, d_out, d_counters);
+    // scenes without a Csg run the instantiation that carries no crossing lists (fewer registers, no local memory)
+    if (sc.n_csg > 0) {
+        if (instrumented) k_rtc_render<true, true><<<blocks, 128, 0, stream>>>(sc, c, jt, d_out, d_counters);
+        else k_rtc_render<false, true><<<blocks, 128, 0, stream>>>(sc, c, jt, d_out, d_counters);
+    } else {
+        if (instrumented) k_rtc_render<true, false><<<blocks, 128, 0, stream>>>(sc, c, jt, d_out, d_counters);
+        else k_rtc_render<false, false><<<blocks, 128, 0, stream>>>(sc, c, jt, d_out, d_counters);
+    }
     return cudaGetLastError();
 }
 
@@ -709,8 +769,13 @@ cudaError_t launch_rtc_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t 
                              Counters* d_counters, bool instrumented, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     unsigned blocks = (unsigned)((n + 127) / 128);
-    if (instrumented) k_rtc_trace<true><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
-    else k_rtc_trace<false><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+    if (sc.n_csg > 0) {
+        if (instrumented) k_rtc_trace<true, true><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+        else k_rtc_trace<false, true><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+    } else {
+        if (instrumented) k_rtc_trace<true, false><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+        else k_rtc_trace<false, false><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
+    }
     return cudaGetLastError();
 }
 

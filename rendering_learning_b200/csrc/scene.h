@@ -37,7 +37,8 @@ struct RtcPrim {
     float4 pat[3];   // object -> pattern space rows (pattern.inv); identity if no pattern
     float ymin, ymax;  // cylinder / cone truncation (+-inf when None)
     int kind, flags;   // flags bit0 = closed
-    int material, node, pad0, pad1;
+    int material, node;
+    int csg_first, csg_count;  // DevScene.csg[csg_first .. +csg_count): the CSG nodes above this leaf, post-order (0 = none)
 };
 
 // triangle: traversal data (48 B) and shading data (64 B) in separate arrays
@@ -101,6 +102,7 @@ struct DevScene {
     int n_tris, n_spheres, n_quads;
     int n_bvh_prims, n_bvh_nodes;  // traversal nodes (>= 1 when n_bvh_prims >= 1)
     int n_big;                     // OW: leaf refs tested brute force before the traversal
+    int n_csg;                     // RTC: CSG nodes
     int n_materials, n_textures, n_lights, n_images, n_xforms;
     int has_transparency;
     int max_reflection_depth;
@@ -119,6 +121,7 @@ struct DevScene {
     const DevLight* lights;
     const BvhNode* nodes;
     const int* big_refs;
+    const int4* csg;  // (operation, lo, mid, hi): left child = prims [lo, mid), right child = prims [mid, hi)
 };
 
 // host-side result of flattening
@@ -141,6 +144,7 @@ struct FlatScene {
     std::vector<int> bvh_ref;      // [n]
     std::vector<int> bvh_node_id;  // [n]
     std::vector<int> big_refs;     // OW leaf refs kept out of the LBVH (OW_BIG_RADIUS)
+    std::vector<int4> csg;         // RTC CSG nodes, post-order
     int has_transparency = 0;
     int max_reflection_depth = 5;
     float void_color[3] = {0, 0, 0};
