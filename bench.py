@@ -303,16 +303,20 @@ def main():
 
         def e2e_step():
             out = e2e_out
+            t0 = time.perf_counter()
+            d2 = ow.lower_world(world)  # the public call lowers the tree every time
+            d2.freeze()
+            t1 = time.perf_counter()
+            ctx.scene_upload(d2)
+            t2 = time.perf_counter()
             if world_size == 1:
-                d2 = ow.lower_world(world)  # the public call lowers the tree every time
-                ctx.scene_upload(d2)
                 ctx.render_ow(cam, 0, out=out)
             else:
-                d2 = ow.lower_world(world)
-                ctx.scene_upload(d2)
                 step(10_000 + counter[0])
                 if rank == 0:
                     e2e_pinned.copy_(frame, non_blocking=False)
+            t3 = time.perf_counter()
+            e2e_phases.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3])
             return desc.nbytes(), out_bytes
     else:
         scene = wl["scene"]()
@@ -339,17 +343,24 @@ def main():
             return ctx.render_rtc_device(cam, 1, [(0, 0, W, H, 0, 1)], frame.data_ptr(), stream)
 
         def e2e_step():
+            t0 = time.perf_counter()
             d2 = scene.world.lower()
+            d2.freeze()
+            t1 = time.perf_counter()
             ctx.scene_upload(d2)
+            t2 = time.perf_counter()
             if world_size == 1:
                 ctx.render_rtc(cam, 1, out=e2e_out)
             else:
                 step(10_000 + counter[0])
                 if rank == 0:
                     e2e_pinned.copy_(frame, non_blocking=False)
+            t3 = time.perf_counter()
+            e2e_phases.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3])
             return desc.nbytes(), out_bytes
 
     e2e_pinned = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    e2e_phases = []
     e2e_out = e2e_pinned.numpy()
 
     # ---- warm-up ----
@@ -395,6 +406,7 @@ def main():
     e2e_step()
     ctx.synchronize()
     barrier()
+    e2e_phases.clear()
     t0 = time.perf_counter()
     for _ in range(e2e_n):
         h2d, d2h = e2e_step()
@@ -449,6 +461,9 @@ def main():
             "clocks": clocks, "gpu_launches": total_launches,
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_n,
+                    "phases_ms_rank0": {"lower_tree": float(np.mean([p[0] for p in e2e_phases])),
+                                        "scene_upload": float(np.mean([p[1] for p in e2e_phases])),
+                                        "render_and_d2h": float(np.mean([p[2] for p in e2e_phases]))},
                     "path": "Camera.render: lower tree -> rl_scene_upload (flatten, H2D, LBVH build) -> render -> D2H (pinned)"},
             "roofline": roofline}
 
