@@ -74,9 +74,10 @@ extern "C" int orc_lbvh_build(const float* aabb, int n, uint64_t* morton, int32_
     std::vector<uint64_t> key(n);
     for (int i = 0; i < n; i++) {
         uint32_t q[3];
+        // one scale for all axes: cubic Morton cells (see k_morton)
+        const float ext = std::fmax(std::fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
         for (int k = 0; k < 3; k++) {
             float c = centroid(aabb[6 * i + k], aabb[6 * i + 3 + k]);
-            float ext = hi[k] - lo[k];
             float t = ext > 0.0f ? (c - lo[k]) / ext : 0.0f;
             float s = std::fmin(std::fmax(t * 2097152.0f, 0.0f), 2097151.0f);
             q[k] = (uint32_t)s;

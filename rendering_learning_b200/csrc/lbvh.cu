@@ -82,9 +82,14 @@ __global__ void k_morton(const float* __restrict__ aabb, int n, const float* __r
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t q[3];
+    // ONE scale for all three axes (the largest centroid extent): the Morton grid cells are cubes.  With a scale per
+    // axis a flat scene (the cover scene: 22 x 0.8 x 22) spends every third bit on a direction in which nothing is
+    // separated; the cubic grid lowers the LBVH's SAH cost from 13.97 to 10.46 there (full-sweep SAH: 9.44) and from
+    // 18.39 to 17.93 on the Cornell box + spot.
+    const float ext = fmaxf(fmaxf(__fsub_rn(bounds[3], bounds[0]), __fsub_rn(bounds[4], bounds[1])),
+                            __fsub_rn(bounds[5], bounds[2]));
     for (int k = 0; k < 3; k++) {
         float c = centroid(aabb[6 * i + k], aabb[6 * i + 3 + k]);
-        float ext = __fsub_rn(bounds[3 + k], bounds[k]);
         float t = ext > 0.0f ? __fdiv_rn(__fsub_rn(c, bounds[k]), ext) : 0.0f;
         float s = fminf(fmaxf(__fmul_rn(t, 2097152.0f), 0.0f), 2097151.0f);
         q[k] = __float2uint_rz(s);

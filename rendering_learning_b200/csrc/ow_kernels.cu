@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
 template <bool COUNT, int MINB, int PRIMS>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
-                                                          int sys_queue, int qbatch, int svc_min, int leaf_min) {
+                                                          int sys_queue, int qbatch, long long q_guided, int svc_min, int leaf_min) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -522,11 +522,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     // the prefetched next batch, whose atomic was issued one batch ago
     __shared__ long long sm_qnext[8], sm_qend[8];
     __shared__ unsigned long long sm_qbase[8];
-    __shared__ int sm_qdry[8];
+    __shared__ int sm_qdry[8], sm_qsize[8];
     const int wid = threadIdx.x >> 5;
     if (lane == 0) {
         sm_qnext[wid] = sm_qend[wid] = 0;
         sm_qdry[wid] = 0;
+        sm_qsize[wid] = qbatch;
         sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
                                   : atomicAdd(queue, (unsigned long long)qbatch);
     }
@@ -566,14 +567,19 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             __syncwarp();
             if (cur_next >= cur_end && !q_dry) {
                 cur_next = (long long)sm_qbase[wid];
-                cur_end = cur_next + qbatch < jt.n_items ? cur_next + qbatch : jt.n_items;
+                const int got = sm_qsize[wid];
+                cur_end = cur_next + got < jt.n_items ? cur_next + got : jt.n_items;
                 __syncwarp();
                 if (cur_next >= jt.n_items) {
                     q_dry = true;
                     cur_end = cur_next;
                 } else if (lane == 0) {
-                    sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
-                                              : atomicAdd(queue, (unsigned long long)qbatch);
+                    // guided self-scheduling: full batches while the queue is long, one item per lane near its end,
+                    // so the last warps to finish hold little work (the tail was 5-7 ms of a 25 ms 8-GPU step)
+                    const int want = jt.n_items - cur_next > q_guided ? qbatch : 32;
+                    sm_qsize[wid] = want;
+                    sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)want)
+                                              : atomicAdd(queue, (unsigned long long)want);
                 }
             }
             long long avail = cur_end - cur_next;
@@ -719,7 +725,21 @@ __global__ void __launch_bounds__(128) k_ow_trace(DevScene sc, const rl_ray* __r
 
 }  // namespace
 
-int ow_num_chunks(int spp) { return spp <= 0 ? 1 : (spp + 31) / 32; }
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Samples are cut into chunks of >= 8 (at most 64 chunks): the chunk is the unit of work a lane owns, so it bounds both
+// the load-balancing tail (a 32-sample item was 1.7 ms of lane time, 10 % of an 8-GPU cover-scene step) and the size
+// of the partial-sum buffer (<= 64 frames).  A function of spp alone, so the image stays independent of the schedule.
+int ow_num_chunks(int spp) {
+    if (spp <= 0) return 1;
+    static const int min_chunk = env_int("RL_OW_CHUNK", 8);  // experiments only: every rank must agree
+    int per_chunk = (spp + 63) / 64;
+    if (per_chunk < min_chunk) per_chunk = min_chunk;
+    return (spp + per_chunk - 1) / per_chunk;
+}
 
 int ow_image_height(const rl_ow_camera* c) {
     double h = (double)c->image_width / c->aspect_ratio;
@@ -775,10 +795,6 @@ static OwCam make_cam(const rl_ow_camera* p, uint32_t first_sample) {
     return c;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
                              float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
@@ -802,7 +818,7 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     static const int svc_min = env_int("RL_OW_SVC", 16), leaf_min = env_int("RL_OW_LEAF", 12);
     static const int generic = env_int("RL_OW_GENERIC", 0);  // 1: never pick the spheres-only instantiation
     typedef void (*K3)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
-    typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, int, int);
+    typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
     K3 k3 = nullptr;
     K5 k4 = nullptr;
     const bool spheres_only = !generic && sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0;
@@ -830,8 +846,10 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
     long long per_warp = jt.n_items / (grid * 8 * 4);
     int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
+    // below this many remaining items a warp reserves 32 instead of qbatch (a shared queue feeds up to 8 GPUs)
+    const long long q_guided = grid * 8 * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
     if (k3) k3<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch);
-    else k4<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch, svc_min, leaf_min);
+    else k4<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch, q_guided, svc_min, leaf_min);
     return cudaGetLastError();
 }
 
