@@ -268,7 +268,7 @@ def main():
         cam = params.abi()
         ctx.scene_upload(desc)
         W, H, nc = cam.image_width, ctx.ow_image_height(cam), ctx.ow_num_chunks(cam)
-        partial = torch.zeros((nc, H, W, 3), dtype=torch.float32, device=dev)
+        partial = torch.zeros((nc, H, W, 4), dtype=torch.float32, device=dev)
         frame = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
         jobs = rd.jobs_for(W, H, nc, world_size) if world_size > 1 else [(0, 0, W, H, 0, nc)]
         samples = W * H * params.samples_per_pixel

@@ -267,7 +267,8 @@ int rl_ow_num_chunks(const rl_ow_camera* cam);
 /* Device-resident variants used for multi-GPU sharding: render only `jobs`, accumulate into device
  * buffers that the caller owns (e.g. torch tensors) so the framebuffer can be gathered with NCCL.
  *   RTC: d_out_rgb [H][W][3] f32, pixels outside the jobs are left untouched.
- *   OW : d_partial [n_chunks][H][W][3] f32 per-chunk partial sums (untouched outside the jobs);
+ *   OW : d_partial [n_chunks][H][W][4] f32 per-chunk partial sums, rgb + one pad float so that a finished item is
+ *        ONE 16-byte store (untouched outside the jobs);
  *        rl_ow_reduce_device folds the chunks in order into d_out_rgb_sum [H][W][3].
  * `stream` is a cudaStream_t; 0 = the ctx's own non-blocking stream (pass cudaStreamLegacy, 0x1, for the
  * legacy default stream).  With stats == NULL the call only LAUNCHES (asynchronous); errors and overflows
@@ -291,7 +292,7 @@ int rl_ow_reduce_device(rl_ctx* ctx, const rl_ow_camera* cam, const void* d_part
 int rl_queue_export(rl_ctx* ctx, void* handle64);
 int rl_queue_import(rl_ctx* ctx, const void* handle64);
 int rl_queue_reset(rl_ctx* ctx, void* stream);
-/* Fused gather: the owner also exports its [n_chunks][H][W][3] partial-sum buffer; with d_partial == NULL
+/* Fused gather: the owner also exports its [n_chunks][H][W][4] partial-sum buffer; with d_partial == NULL
  * rl_render_ow_shared stores every finished item straight into the OWNER's HBM over NVLink (each slot is
  * written exactly once, by whichever GPU popped it), so no separate framebuffer collective is needed — only
  * a rendezvous before rl_ow_reduce_device(d_partial = NULL) folds the chunks on the owner. */

@@ -654,7 +654,7 @@ int rl_render_ow(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, floa
     int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
     size_t frame = (size_t)cam->image_width * H * 3 * sizeof(float);
     CK(c, cudaSetDevice(c->device));
-    CK(c, c->partial.reserve(frame * nc));
+    CK(c, c->partial.reserve(frame / 3 * 4 * nc));  // [n_chunks][H][W] float4
     CK(c, c->frame.reserve(frame));
     rl_job job{0, 0, cam->image_width, H, 0, nc};
     rl_stats st{};

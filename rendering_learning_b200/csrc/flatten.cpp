@@ -11,6 +11,7 @@
 //         nodes are replaced by one LBVH over all bounded primitives (closest-hit semantics, bvh.rs:81-90).
 //
 // All composition / inversion is done in f64 and rounded to f32 once, at the end.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -415,12 +416,17 @@ struct Flattener {
                 if (!(nn > 1e-16)) return fail(RL_E_INVALID, "Failed to find normal because u and v were parallel");
                 double un[3] = {n[0], n[1], n[2]};
                 normalize3(un);
+                // plane.rs:51-80 evaluates alpha = w . (h x v), beta = w . (u x h) with h = p - q, w = n / (n . n).  By the
+                // cyclic symmetry of the triple product alpha = h . (v x w) and beta = h . (w x u): two dot products with
+                // vectors precomputed here in f64 (the device test is 3 loads + ~25 instructions instead of 5 + ~50)
+                double W[3] = {n[0] / nn, n[1] / nn, n[2] / nn};
+                double A[3] = {V[1] * W[2] - V[2] * W[1], V[2] * W[0] - V[0] * W[2], V[0] * W[1] - V[1] * W[0]};
+                double B[3] = {W[1] * U[2] - W[2] * U[1], W[2] * U[0] - W[0] * U[2], W[0] * U[1] - W[1] * U[0]};
                 OwQuad o;
-                o.q = make_float4((float)Q[0], (float)Q[1], (float)Q[2], (float)(un[0] * Q[0] + un[1] * Q[1] + un[2] * Q[2]));
-                o.u = make_float4((float)U[0], (float)U[1], (float)U[2], as_f(nd.material));
-                o.v = make_float4((float)V[0], (float)V[1], (float)V[2], 0.0f);
-                o.n = make_float4((float)un[0], (float)un[1], (float)un[2], 0.0f);
-                o.w = make_float4((float)(n[0] / nn), (float)(n[1] / nn), (float)(n[2] / nn), 0.0f);
+                o.n = make_float4((float)un[0], (float)un[1], (float)un[2], (float)(un[0] * Q[0] + un[1] * Q[1] + un[2] * Q[2]));
+                o.a = make_float4((float)A[0], (float)A[1], (float)A[2], (float)(A[0] * Q[0] + A[1] * Q[1] + A[2] * Q[2]));
+                o.b = make_float4((float)B[0], (float)B[1], (float)B[2], (float)(B[0] * Q[0] + B[1] * Q[1] + B[2] * Q[2]));
+                o.m = make_int4(nd.material, 0, 0, 0);
                 int idx = (int)fs->quads.size();
                 fs->quads.push_back(o);
                 fs->quad_node.push_back(id);
@@ -510,6 +516,58 @@ bool invert_affine_4x4(const double* m16, double* inv12, std::string* err) {
     return true;
 }
 
+// Primitives that are large against the rest of the scene (the walls and the light of a Cornell box around a mesh)
+// leave the LBVH for the brute-force "big" list (scene.h OW_MAX_BIG): inside the hierarchy their boxes overlap
+// everything, so every ray walks them anyway, while outside it a ray that misses the remaining geometry's root box
+// ends its traversal after one node.  Rule: of the OW_MAX_BIG largest boxes (by surface area), those whose area is at
+// least a quarter of the area of the box around all the OTHER primitives.
+static double box_area(const float* b) {
+    double x = (double)b[3] - b[0], y = (double)b[4] - b[1], z = (double)b[5] - b[2];
+    return 2.0 * (x * y + y * z + x * z);
+}
+static void select_big_prims(FlatScene* fs) {
+    const int n = (int)fs->bvh_ref.size();
+    const int room = OW_MAX_BIG - (int)fs->big_refs.size();
+    if (n < 2 * OW_MAX_BIG || room <= 0) return;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    auto bigger = [&](int a, int b) {
+        double sa = box_area(&fs->bvh_aabb[6 * a]), sb = box_area(&fs->bvh_aabb[6 * b]);
+        return sa > sb || (sa == sb && a < b);
+    };
+    std::partial_sort(order.begin(), order.begin() + room, order.end(), bigger);
+    std::vector<char> cand(n, 0);
+    for (int k = 0; k < room; k++) cand[order[k]] = 1;
+    float rest[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < n; i++) {
+        if (cand[i]) continue;
+        for (int k = 0; k < 3; k++) {
+            rest[k] = std::fmin(rest[k], fs->bvh_aabb[6 * i + k]);
+            rest[3 + k] = std::fmax(rest[3 + k], fs->bvh_aabb[6 * i + 3 + k]);
+        }
+    }
+    const double limit = 0.25 * box_area(rest);
+    std::vector<char> big(n, 0);
+    bool any = false;
+    for (int k = 0; k < room; k++)
+        if (box_area(&fs->bvh_aabb[6 * order[k]]) >= limit) big[order[k]] = 1, any = true;
+    if (!any) return;
+    std::vector<float> aabb;
+    std::vector<int> ref, node;
+    for (int i = 0; i < n; i++) {
+        if (big[i]) {
+            fs->big_refs.push_back(fs->bvh_ref[i]);
+            continue;
+        }
+        aabb.insert(aabb.end(), fs->bvh_aabb.begin() + 6 * i, fs->bvh_aabb.begin() + 6 * i + 6);
+        ref.push_back(fs->bvh_ref[i]);
+        node.push_back(fs->bvh_node_id[i]);
+    }
+    fs->bvh_aabb.swap(aabb);
+    fs->bvh_ref.swap(ref);
+    fs->bvh_node_id.swap(node);
+}
+
 int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err) {
     if (!d || d->abi_version != RL_B200_ABI_VERSION) {
         *err = "scene description missing or ABI version mismatch";
@@ -537,6 +595,7 @@ int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err) {
             return RL_E_INVALID;
         }
         if (!f.ow_node(d->roots[0], aff_identity(), aff_identity(), false, 0)) return f.rc;
+        select_big_prims(out);
     }
     return RL_OK;
 }

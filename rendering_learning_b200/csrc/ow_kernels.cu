@@ -154,16 +154,16 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
     } else if (PRIMS & PRIMS_QUADS) {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
         if (ref == self_ref) return;
         const OwQuad& qd = sc.quads[idx];
-        float4 n4 = qd.n, q4 = qd.q;
+        float4 n4 = qd.n;
         if (COUNT) lc.prims++;
         float denom = dot(f3(n4), d);
         if (fabsf(denom) < 1e-8f) return;
-        float t = (q4.w - dot(f3(n4), o)) / denom;
+        float t = (n4.w - dot(f3(n4), o)) / denom;
         if (!(t >= tmin && t < h.t)) return;
-        float3 ph = fma3(d, t, o) - f3(q4);
-        float3 w = f3(qd.w);
-        float alpha = dot(w, cross(ph, f3(qd.v)));
-        float beta = dot(w, cross(f3(qd.u), ph));
+        float3 ip = fma3(d, t, o);
+        float4 a4 = qd.a, b4 = qd.b;
+        float alpha = dot(f3(a4), ip) - a4.w;
+        float beta = dot(f3(b4), ip) - b4.w;
         if (!(0.0f <= alpha && alpha <= 1.0f && 0.0f <= beta && beta <= 1.0f)) return;
         h.t = t;
         h.ref = ref;
@@ -281,8 +281,8 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
         const OwQuad& qd = sc.quads[idx];
         outward = f3(qd.n);
         float3 ip = fma3(p.d, h.t, p.o);
-        pos = ip - outward * (dot(outward, ip) - qd.q.w);  // snapped onto the plane
-        mat_id = __float_as_int(qd.u.w);
+        pos = ip - outward * (dot(outward, ip) - qd.n.w);  // snapped onto the plane
+        mat_id = qd.m.x;
     }
     bool front = dot(p.d, outward) <= 0.0f;  // hittable/mod.rs:32-38
     normal = front ? outward : -outward;
@@ -394,10 +394,8 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
     while (true) {
         // ---- retire finished items, refill idle lanes (warp-aggregated queue pop) ----
         if (has_item && !alive && s == s_end) {
-            size_t idx = (((size_t)chunk * cam.height + y) * cam.width + x) * 3;
-            partial[idx + 0] = acc.x;
-            partial[idx + 1] = acc.y;
-            partial[idx + 2] = acc.z;
+            size_t idx = ((size_t)chunk * cam.height + y) * cam.width + x;
+            reinterpret_cast<float4*>(partial)[idx] = make_float4(acc.x, acc.y, acc.z, 0.0f);  // one 16-byte store
             has_item = false;
         }
         bool need = !has_item && !done;
@@ -553,10 +551,10 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             }
         }
         if (svc && has_item && !alive && s == sm_send[tid]) {
-            size_t idx = (((size_t)sm_chunk[tid] * cam.height + sm_y[tid]) * cam.width + sm_x[tid]) * 3;
-            partial[idx + 0] = sm_acc[0][tid];
-            partial[idx + 1] = sm_acc[1][tid];
-            partial[idx + 2] = sm_acc[2][tid];
+            // ONE 16-byte store per finished item (over NVLink when the buffer is rank 0's: three 4-byte stores per
+            // item were 134 M small remote writes per 8-GPU cover-scene step)
+            size_t idx = ((size_t)sm_chunk[tid] * cam.height + sm_y[tid]) * cam.width + sm_x[tid];
+            reinterpret_cast<float4*>(partial)[idx] = make_float4(sm_acc[0][tid], sm_acc[1][tid], sm_acc[2][tid], 0.0f);
             has_item = false;
         }
         const bool need = svc && !has_item;
@@ -690,13 +688,20 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     lc.flush(counters);
 }
 
-// fold the per-chunk partial sums in chunk order
-__global__ void k_ow_reduce(const float* __restrict__ partial, float* __restrict__ out, size_t n, int n_chunks) {
+// fold the per-chunk partial sums ([chunk][pixel] float4) in chunk order into [pixel][3]
+__global__ void k_ow_reduce(const float4* __restrict__ partial, float* __restrict__ out, size_t n_pixels, int n_chunks) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.0f;
-    for (int c = 0; c < n_chunks; c++) s += partial[(size_t)c * n + i];
-    out[i] = s;
+    if (i >= n_pixels) return;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    for (int c = 0; c < n_chunks; c++) {
+        float4 v = partial[(size_t)c * n_pixels + i];
+        r += v.x;
+        g += v.y;
+        b += v.z;
+    }
+    out[3 * i + 0] = r;
+    out[3 * i + 1] = g;
+    out[3 * i + 2] = b;
 }
 
 template <bool COUNT>
@@ -854,9 +859,9 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
 }
 
 cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream) {
-    size_t n = (size_t)cam->image_width * ow_image_height(cam) * 3;
+    size_t n = (size_t)cam->image_width * ow_image_height(cam);
     int nc = ow_num_chunks(cam->samples_per_pixel);
-    k_ow_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_partial, d_out, n, nc);
+    k_ow_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(d_partial), d_out, n, nc);
     return cudaGetLastError();
 }
 

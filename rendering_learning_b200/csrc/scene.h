@@ -61,14 +61,12 @@ struct OwSphere {  // 32 B
     float4 c;   // centre at time 0, w = radius
     float4 dc;  // centre(1) - centre(0), w = material (int bits)
 };
-struct OwQuad {  // 80 B
-    float4 q;  // xyz, w = d = n . q
-    float4 u;  // xyz, w = material (int bits)
-    float4 v;  // xyz
-    float4 n;  // unit normal
-    float4 w;  // n_raw / (n_raw . n_raw)
+struct OwQuad {  // 64 B; the intersection test reads the first 48
+    float4 n;  // unit normal, w = d = n . q
+    float4 a;  // alpha = a.xyz . p - a.w, with a.xyz = v x w and a.w = a.xyz . q   (w = n_raw / (n_raw . n_raw))
+    float4 b;  // beta  = b.xyz . p - b.w, with b.xyz = w x u and b.w = b.xyz . q
+    int4 m;    // x = material
 };
-
 struct DevMaterial {  // 48 B
     float4 color;  // rgb (RTC surface colour / OW metal albedo), w = texture index (int bits, -1 none)
     float4 a;      // RTC: ambient, diffuse, specular, shininess | OW: fuzz, refractive_index, 0, 0

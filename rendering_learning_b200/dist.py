@@ -92,7 +92,7 @@ def render_ow_distributed(ctx, cam, first_sample: int, jobs: Sequence[Job], part
                           store=None, static: bool = False):
     """One OW render sharded over the ranks of the default process group.
 
-    partial: [n_chunks, H, W, 3] f32 device tensor on every rank; out: [H, W, 3] f32 (written on rank 0).
+    partial: [n_chunks, H, W, 4] f32 device tensor (rgb + pad) on every rank; out: [H, W, 3] f32 (written on rank 0).
     Returns the job ids this rank rendered."""
     import torch
     import torch.distributed as dist
