@@ -92,7 +92,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
                                              int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc) {
     const float3 o = pre.o, d = pre.d;
     int type = ref_type(ref), idx = ref_index(ref);
-    if (PRIMS == PRIMS_SPHERES || type == REF_SPHERE) {  // sphere.rs:34-75
+    if (PRIMS == PRIMS_SPHERES || ((PRIMS & PRIMS_SPHERES) && type == REF_SPHERE)) {  // sphere.rs:34-75
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
         if (COUNT) lc.prims++;
         float3 center = fma3(f3(dc), time, f3(c));
@@ -173,17 +173,28 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
     }
 }
 
-// same test from (o, d) alone: the v4 kernel does not keep the watertight shear constants live across its service
-// rounds; they are rebuilt at the triangle tests (0.5 per ray on the Cornell box, none on the cover scene)
+// same test from (o, d) plus the watertight shear constants the v5 kernel computes once per ray (make_pre per triangle
+// test was 15 % of the Cornell-box warp instructions, at 4-6 lanes: profiles/r01_ncu_k_ow_render_v5_c5.json)
+struct TriShear {
+    int k;  // kx | ky << 2 | kz << 4
+    float Sx, Sy, Sz;
+};
+__device__ __forceinline__ TriShear make_shear(float3 o, float3 d) {
+    RayPre r = make_pre(o, d);
+    TriShear t;
+    t.k = r.kx | (r.ky << 2) | (r.kz << 4);
+    t.Sx = r.Sx; t.Sy = r.Sy; t.Sz = r.Sz;
+    return t;
+}
 template <bool COUNT, int PRIMS>
-__device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, float3 o, float3 d, float time, int self_ref,
-                                                float tmin, OwHit& h, LocalCount<COUNT>& lc) {
+__device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, float3 o, float3 d, const TriShear& sh, float time,
+                                                int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc) {
     RayPre pre;
-    if ((PRIMS & PRIMS_TRIS) && ref_type(ref) == REF_TRI) {
-        pre = make_pre(o, d);
-    } else {
-        pre.o = o;
-        pre.d = d;
+    pre.o = o;
+    pre.d = d;
+    if (PRIMS & PRIMS_TRIS) {
+        pre.kx = sh.k & 3; pre.ky = (sh.k >> 2) & 3; pre.kz = (sh.k >> 4) & 3;
+        pre.Sx = sh.Sx; pre.Sy = sh.Sy; pre.Sz = sh.Sz;
     }
     ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, dot(d, d), time, self_ref, tmin, h, lc);
 }
@@ -255,7 +266,7 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
     int mat_id = 0;
     bool uv_from_sphere = false;
     float3 outward = f3(0.0f, 1.0f, 0.0f);
-    if (PRIMS == PRIMS_SPHERES || type == REF_SPHERE) {
+    if (PRIMS == PRIMS_SPHERES || ((PRIMS & PRIMS_SPHERES) && type == REF_SPHERE)) {
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
         float3 center = fma3(f3(dc), p.time, f3(c));
         float3 q = fma3(p.d, h.t, p.o) - center;
@@ -514,6 +525,8 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     int stack_node[BVH_STACK];
     float3 inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
     float tmin = 0.0f;
+    TriShear shear;
+    shear.k = 0; shear.Sx = shear.Sy = shear.Sz = 0.0f;
     OwHit hit;
     hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
     // queue (warp-uniform, one slot per warp in shared memory): the current reserved batch [next, end) and the base of
@@ -627,11 +640,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             inv_d = f3(1.0f / p.d.x, 1.0f / p.d.y, 1.0f / p.d.z);
             oi = p.o * inv_d;
             tmin = ow_tmin(p);
+            if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
             sp = 0;
             if (COUNT) lc.rays++;
-            for (int k = 0; k < sc.n_big; k++)  // OW_BIG_RADIUS spheres: once per ray, here, with the serviced lanes
-                ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, p.time, p.self_ref, tmin, hit, lc);
+            for (int k = 0; k < sc.n_big; k++)  // the big list: once per ray, here, with the serviced lanes
+                ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc);
             node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
         }
         const unsigned m_done = __ballot_sync(FULL, done);
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
         while (true) {
             // leaf round: every lane parked at a leaf tests it and pops
             if (node < 0 && node != TRAV_END) {
-                ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, p.time, p.self_ref, tmin, hit, lc);
+                ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc);
                 node = sp > 0 ? stack_node[--sp] : TRAV_END;
             }
             const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));
@@ -827,14 +841,20 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     K3 k3 = nullptr;
     K5 k4 = nullptr;
     const bool spheres_only = !generic && sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0;
-    // measured (gpurun_out/sweep_ow4.log): the spheres-only build fits 64 registers (4 CTAs/SM) with 18 B of spills and
-    // wins there; the generic build is better at 80 registers (3 CTAs/SM)
-    const int minb = minb_env ? minb_env : (spheres_only ? 4 : 3);
+    const bool no_spheres = !generic && sc.n_spheres == 0;
+    // measured (profiles/r01_sweep_ow_v5.log and the C5 runs after it): the spheres-only and the no-spheres builds fit
+    // 64 registers (4 CTAs/SM) with 18 / 86 B of spills and win there (C5 @64 spp: 66.7 vs 69.4 ms); the build that
+    // carries every primitive kind is better at 80 registers (3 CTAs/SM)
+    const int minb = minb_env ? minb_env : ((spheres_only || no_spheres) ? 4 : 3);
+    constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
     if (variant == 3) {
         k3 = instrumented ? (K3)k_ow_render<true, 1, 4> : (K3)k_ow_render<false, 1, 4>;
     } else if (spheres_only) {
         if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_SPHERES> : (K5)k_ow_render5<false, 4, PRIMS_SPHERES>;
         else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_SPHERES> : (K5)k_ow_render5<false, 3, PRIMS_SPHERES>;
+    } else if (no_spheres) {
+        if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_FLAT> : (K5)k_ow_render5<false, 4, PRIMS_FLAT>;
+        else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FLAT> : (K5)k_ow_render5<false, 3, PRIMS_FLAT>;
     } else {
         if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_ALL> : (K5)k_ow_render5<false, 4, PRIMS_ALL>;
         else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_ALL> : (K5)k_ow_render5<false, 3, PRIMS_ALL>;
