@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 1
+#define RL_B200_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------------------------- */
 enum {
@@ -68,7 +68,9 @@ enum {
     RL_OW_TRANSFORM = 35,  /* params: M[9] Minv[9] (3x3 row-major); child_begin = child node id       */
     RL_OW_TRANSLATE = 36,  /* params: offset[3]; child_begin = child node id                          */
     RL_OW_BVH = 37,        /* children[child_begin .. child_end) — Bvh::new(vec)                      */
-    RL_OW_LIST = 38        /* children[child_begin .. child_end) — slice / array of hittables         */
+    RL_OW_LIST = 38,       /* children[child_begin .. child_end) — slice / array of hittables         */
+    RL_OW_CONSTANT_MEDIUM = 39 /* hittable/constant_medium.rs:8-23: params: density; material = the phase
+                              * function; child_begin = boundary node id                              */
 };
 
 enum { RL_CSG_UNION = 0, RL_CSG_INTERSECTION = 1, RL_CSG_DIFFERENCE = 2 };
@@ -87,7 +89,8 @@ enum {
     RL_MAT_OW_LAMBERTIAN = 16,   /* OW/src/material.rs:69-97   (texture) */
     RL_MAT_OW_METAL = 17,        /* OW/src/material.rs:99-127  (color = albedo, fuzz) */
     RL_MAT_OW_DIELECTRIC = 18,   /* OW/src/material.rs:134-170 (refractive_index) */
-    RL_MAT_OW_DIFFUSE_LIGHT = 19 /* OW/src/material.rs:178-195 (texture) */
+    RL_MAT_OW_DIFFUSE_LIGHT = 19,/* OW/src/material.rs:178-195 (texture) */
+    RL_MAT_OW_ISOTROPIC = 20     /* OW/src/material.rs:197-221 (texture) */
 };
 
 typedef struct rl_material {
@@ -105,15 +108,16 @@ enum {
     RL_TEX_RTC_RING = 4,     /* RTC/src/scene/pattern/ring.rs:20-28      */
     RL_TEX_OW_SOLID = 16,    /* OW/src/texture.rs:15-23 (a = albedo)     */
     RL_TEX_OW_CHECKER = 17,  /* OW/src/texture.rs:25-55 (tex_a = even, tex_b = odd, scale) */
-    RL_TEX_OW_IMAGE = 18     /* OW/src/texture.rs:58-82 (image index)    */
+    RL_TEX_OW_IMAGE = 18,    /* OW/src/texture.rs:58-82 (image index)    */
+    RL_TEX_OW_NOISE = 19     /* OW/src/texture.rs:84-94 (image = index into perlins[], scale) */
 };
 
 typedef struct rl_texture {
     int32_t kind;
     int32_t tex_a, tex_b; /* OW checker: even / odd texture indices */
-    int32_t image;        /* OW image: index into images[] */
+    int32_t image;        /* OW image: index into images[]; OW noise: index into perlins[] */
     double a[3], b[3];
-    double scale;         /* OW checker scale (the reference stores 1/scale) */
+    double scale;         /* OW checker scale (the reference stores 1/scale); OW noise scale */
     double transform[16]; /* RTC pattern: forward 4x4 */
 } rl_texture;
 
@@ -121,6 +125,11 @@ typedef struct rl_image {
     int32_t width, height;
     const float* rgb; /* width*height*3, row-major, top row first, LINEAR colour (image::Rgb32FImage) */
 } rl_image;
+
+typedef struct rl_perlin {  /* OW/src/perlin.rs:9-14 — the tables Perlin::new(rng) drew */
+    double randvec[256][3];
+    int32_t perm_x[256], perm_y[256], perm_z[256];
+} rl_perlin;
 
 typedef struct rl_light {   /* RTC/src/scene/light.rs:3-7 */
     double position[3];
@@ -140,6 +149,7 @@ typedef struct rl_scene_desc {
     const rl_light* lights;        int32_t n_lights; /* RTC World.lights */
     int32_t max_reflection_depth;  /* RTC World.max_reflection_depth (world.rs:26-31) */
     double void_color[3];          /* RTC World.void_color */
+    const rl_perlin* perlins;      int32_t n_perlins; /* OW Noise textures (ABI version 2) */
 } rl_scene_desc;
 
 /* ---- cameras --------------------------------------------------------------------------------- */

@@ -170,6 +170,16 @@ def ow_trace(desc, rays: np.ndarray, threads: int = 0):
     return node, t, uv
 
 
+def ow_tex_value(desc, tex: int, uvp: np.ndarray) -> np.ndarray:
+    """Texture::value at rows (u, v, x, y, z)"""
+    d = desc.freeze()
+    uvp = np.ascontiguousarray(uvp, np.float64).reshape(-1, 5)
+    out = np.zeros((uvp.shape[0], 3), np.float64)
+    if lib().orc_ow_tex_value(C.byref(d), C.c_int(tex), C.c_uint64(uvp.shape[0]), _dp(uvp), _dp(out)) != 0:
+        raise RuntimeError("orc_ow_tex_value failed")
+    return out
+
+
 def ow_camera_rays(cam: A.rl_ow_camera) -> np.ndarray:
     h = ow_image_height(cam)
     rays = np.zeros((h * cam.image_width, 7), np.float64)

@@ -239,6 +239,11 @@ inline V3 mul(const M3& a, V3 v) {  // matrix.rs:42-60
     return {o[0], o[1], o[2]};
 }
 
+// ConstantMedium::hit draws from the process-global RNG in the reference (constant_medium.rs:52-55, its own TODO: not
+// repeatable).  The oracle draws from the path's seeded stream instead, handed over through this pointer by ray_color;
+// with no stream attached (orc_ow_trace) a medium is never hit.
+static thread_local ChaCha8Rng* tl_medium_rng = nullptr;
+
 struct Scene;
 struct Obj {
     int kind, node, material = -1;
@@ -250,7 +255,9 @@ struct Obj {
     bool has_uv = false, has_n = false; V3 n1, n2, n3; double uv[6];
     // transform / translate
     M3 M, Minv, MinvT; V3 offset;
-    // children (list / bvh node)
+    // constant medium
+    double neg_inv_density = 0.0;
+    // children (list / bvh node / the boundary of a medium)
     std::vector<std::unique_ptr<Obj>> kids;
     bool is_bvh_leaf = false;
 };
@@ -354,6 +361,13 @@ struct Scene {
                 if (hs.empty()) { ok = false; break; }
                 o = bvh_new(std::move(hs));
                 o->node = id;
+                break;
+            }
+            case RL_OW_CONSTANT_MEDIUM: {  // constant_medium.rs:14-22, bounding_box 85-87
+                if (!p || nd.child_begin < 0) { ok = false; break; }
+                o->neg_inv_density = -1.0 / p[0];
+                o->kids.push_back(build(nd.child_begin));
+                o->bbox = o->kids[0]->bbox;
                 break;
             }
             default: ok = false;
@@ -505,6 +519,27 @@ struct Scene {
                 rec->p = rec->p + o.offset;
                 return true;
             }
+            case RL_OW_CONSTANT_MEDIUM: {  // constant_medium.rs:28-83
+                if (!tl_medium_rng) return false;
+                const Obj& b = *o.kids[0];
+                HitRecord rec1, rec2;
+                if (!hit(b, r, {-INF, INF}, &rec1)) return false;
+                if (!hit(b, r, {rec1.t + 1e-4, INF}, &rec2)) return false;
+                rec1.t = std::fmax(rec1.t, rt.min);
+                rec2.t = std::fmin(rec2.t, rt.max);
+                if (rec1.t >= rec2.t) return false;
+                rec1.t = std::fmax(rec1.t, 0.0);
+                double ray_length = length(r.direction);
+                double distance_inside_boundary = (rec2.t - rec1.t) * ray_length;
+                double hit_distance = o.neg_inv_density * std::log(tl_medium_rng->gen_f64());
+                if (hit_distance > distance_inside_boundary) return false;
+                double t = rec1.t + hit_distance / ray_length;
+                rec->p = r.at(t);
+                rec->normal = v3(1.0, 0.0, 0.0);  // arbitrary
+                rec->t = t; rec->u = 0.0; rec->v = 0.0; rec->front = true;
+                rec->material = o.material; rec->node = o.node;
+                return true;
+            }
             case RL_OW_LIST:
                 return hit_slice(o.kids, r, rt, rec);
             case RL_OW_BVH:  // bvh.rs:81-90
@@ -512,6 +547,35 @@ struct Scene {
                 return hit_slice(o.kids, r, rt, rec);
         }
         return false;
+    }
+
+    // perlin.rs:39-63 (noise), 91-115 (perlin_interp), 65-78 (turb)
+    double perlin_noise(const rl_perlin& pn, V3 p) const {
+        double fx = std::floor(p.x), fy = std::floor(p.y), fz = std::floor(p.z);
+        double u = p.x - fx, v = p.y - fy, w = p.z - fz;
+        int i = (int)fx, j = (int)fy, k = (int)fz;
+        double uu = u * u * (3.0 - 2.0 * u), vv = v * v * (3.0 - 2.0 * v), ww = w * w * (3.0 - 2.0 * w);
+        double accum = 0.0;
+        for (int di = 0; di < 2; di++)
+            for (int dj = 0; dj < 2; dj++)
+                for (int dk = 0; dk < 2; dk++) {
+                    const double* c = pn.randvec[pn.perm_x[(i + di) & 255] ^ pn.perm_y[(j + dj) & 255] ^ pn.perm_z[(k + dk) & 255]];
+                    double i_f = di, j_f = dj, k_f = dk;
+                    V3 weight_v = v3(u - i_f, v - j_f, w - k_f);
+                    accum += (i_f * uu + (1.0 - i_f) * (1.0 - uu)) * (j_f * vv + (1.0 - j_f) * (1.0 - vv)) *
+                             (k_f * ww + (1.0 - k_f) * (1.0 - ww)) * dot(v3(c[0], c[1], c[2]), weight_v);
+                }
+        return accum;
+    }
+    double perlin_turb(const rl_perlin& pn, V3 p, int depth) const {
+        double accum = 0.0, weight = 1.0;
+        V3 temp_p = p;
+        for (int i = 0; i < depth; i++) {
+            accum += weight * perlin_noise(pn, temp_p);
+            weight *= 0.5;
+            temp_p = temp_p * 2.0;
+        }
+        return std::fabs(accum);
     }
 
     // texture.rs
@@ -535,6 +599,10 @@ struct Scene {
                 uint32_t j = (uint32_t)(vv * (double)(im.height - 1));
                 const float* px = im.rgb + ((size_t)j * im.width + i) * 3;
                 return v3((double)px[0], (double)px[1], (double)px[2]);
+            }
+            case RL_TEX_OW_NOISE: {  // 89-93
+                const rl_perlin& pn = d->perlins[t.image];
+                return v3(0.5, 0.5, 0.5) * (1.0 + std::sin(t.scale * p.z + 10.0 * perlin_turb(pn, p, 7)));
             }
         }
         return v3(0, 0, 0);
@@ -584,6 +652,11 @@ struct Scene {
                 V3 dir = refl ? reflect(unit, h.normal) : refract(unit, h.normal, ri);
                 *out = {h.p, dir, ray.time};
                 *atten = v3(1, 1, 1);
+                return true;
+            }
+            case RL_MAT_OW_ISOTROPIC: {  // 201-216
+                *out = {h.p, random_unit_vector(rng), ray.time};
+                *atten = tex_value(mt.texture, h.u, h.v, h.p);
                 return true;
             }
             default: return false;  // DiffuseLight never scatters (182-189)
@@ -644,7 +717,10 @@ struct Camera {
         if (depth == 0) return v3(0, 0, 0);
         if (rays) ++*rays;
         HitRecord h;
-        if (sc.hit(*sc.root, r, {1e-10, INF}, &h)) {
+        tl_medium_rng = &rng;
+        bool was_hit = sc.hit(*sc.root, r, {1e-10, INF}, &h);
+        tl_medium_rng = nullptr;
+        if (was_hit) {
             V3 em = sc.emitted(h.material, h.u, h.v, h.p);
             V3 att;
             Ray sr;
@@ -744,6 +820,17 @@ int orc_ow_camera_rays(const rl_ow_camera* cam, double* rays) {
 }
 
 // raw RNG words for known-answer tests: seed, stream, n u64 outputs
+// Texture::value at n points (u, v, x, y, z) — lets the tests pin the Perlin / Noise restatement against the host mirror
+int orc_ow_tex_value(const rl_scene_desc* d, int tex, uint64_t n, const double* uvp, double* rgb) {
+    if (!d || tex < 0 || tex >= d->n_textures) return -1;
+    Scene sc(d);
+    for (uint64_t i = 0; i < n; i++) {
+        V3 c = sc.tex_value(tex, uvp[5 * i], uvp[5 * i + 1], v3(uvp[5 * i + 2], uvp[5 * i + 3], uvp[5 * i + 4]));
+        rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+    }
+    return 0;
+}
+
 int orc_chacha8_u64(uint64_t seed, uint64_t stream, int n, uint64_t* out) {
     ChaCha8Rng rng(seed);
     rng.set_stream(stream);

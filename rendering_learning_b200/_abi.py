@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librl_b200.so")
 
-RL_B200_ABI_VERSION = 1
+RL_B200_ABI_VERSION = 2
 
 RL_OK = 0
 RL_E_INVALID = -1
@@ -42,6 +42,7 @@ RL_OW_TRANSFORM = 35
 RL_OW_TRANSLATE = 36
 RL_OW_BVH = 37
 RL_OW_LIST = 38
+RL_OW_CONSTANT_MEDIUM = 39
 
 RL_CSG_UNION = 0
 RL_CSG_INTERSECTION = 1
@@ -52,6 +53,7 @@ RL_MAT_OW_LAMBERTIAN = 16
 RL_MAT_OW_METAL = 17
 RL_MAT_OW_DIELECTRIC = 18
 RL_MAT_OW_DIFFUSE_LIGHT = 19
+RL_MAT_OW_ISOTROPIC = 20
 
 RL_TEX_RTC_STRIPE = 1
 RL_TEX_RTC_CHECKER3D = 2
@@ -60,6 +62,7 @@ RL_TEX_RTC_RING = 4
 RL_TEX_OW_SOLID = 16
 RL_TEX_OW_CHECKER = 17
 RL_TEX_OW_IMAGE = 18
+RL_TEX_OW_NOISE = 19
 
 
 class rl_node(C.Structure):
@@ -85,6 +88,11 @@ class rl_image(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("rgb", C.POINTER(C.c_float))]
 
 
+class rl_perlin(C.Structure):
+    _fields_ = [("randvec", (C.c_double * 3) * 256), ("perm_x", C.c_int32 * 256),
+                ("perm_y", C.c_int32 * 256), ("perm_z", C.c_int32 * 256)]
+
+
 class rl_light(C.Structure):
     _fields_ = [("position", C.c_double * 3), ("intensity", C.c_double * 3)]
 
@@ -99,7 +107,8 @@ class rl_scene_desc(C.Structure):
                 ("textures", C.POINTER(rl_texture)), ("n_textures", C.c_int32),
                 ("images", C.POINTER(rl_image)), ("n_images", C.c_int32),
                 ("lights", C.POINTER(rl_light)), ("n_lights", C.c_int32),
-                ("max_reflection_depth", C.c_int32), ("void_color", C.c_double * 3)]
+                ("max_reflection_depth", C.c_int32), ("void_color", C.c_double * 3),
+                ("perlins", C.POINTER(rl_perlin)), ("n_perlins", C.c_int32)]
 
 
 class rl_rtc_camera(C.Structure):

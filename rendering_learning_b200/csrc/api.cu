@@ -55,7 +55,7 @@ struct rl_ctx {
     DevBuf prims, tri_verts, tri_shade, xforms, spheres, quads, sphere_node, quad_node, materials, textures,
         images, lights, nodes;
     std::vector<DevBuf> image_texels;
-    DevBuf big_refs, csg, bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
+    DevBuf big_refs, csg, media, medium_refs, perlin_vec, perlin_perm, bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
         node_aabb, lbvh_counters;
     DevScene ds{};
     rl_scene_info info{};
@@ -155,7 +155,7 @@ void rl_destroy(rl_ctx* c) {
     c->shared_partial_own.release();
     c->shared_queue_own.release();
     DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
-                     &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->bvh_aabb,
+                     &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
                      &c->jobs, &c->prefix, &c->frame, &c->partial, &c->rays, &c->hits};
@@ -248,6 +248,10 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     int nn = n >= 2 ? n - 1 : (n == 1 ? 1 : 0);
     CK(c, upload(c->big_refs, fs.big_refs, s));
     CK(c, upload(c->csg, fs.csg, s));
+    CK(c, upload(c->media, fs.media, s));
+    CK(c, upload(c->medium_refs, fs.medium_refs, s));
+    CK(c, upload(c->perlin_vec, fs.perlin_vec, s));
+    CK(c, upload(c->perlin_perm, fs.perlin_perm, s));
     CK(c, upload(c->bvh_aabb, fs.bvh_aabb, s));
     CK(c, upload(c->bvh_ref, fs.bvh_ref, s));
     CK(c, upload(c->bvh_node_id, fs.bvh_node_id, s));
@@ -295,6 +299,8 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     d.n_bvh_nodes = nn;
     d.n_big = (int)fs.big_refs.size();
     d.n_csg = (int)fs.csg.size();
+    d.n_media = (int)fs.media.size();
+    d.n_perlins = (int)fs.perlin_vec.size() / 256;
     d.n_materials = (int)fs.materials.size();
     d.n_textures = (int)fs.textures.size();
     d.n_lights = (int)fs.lights.size();
@@ -318,6 +324,10 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     d.nodes = c->nodes.as<BvhNode>();
     d.big_refs = c->big_refs.as<int>();
     d.csg = c->csg.as<int4>();
+    d.media = c->media.as<OwMedium>();
+    d.medium_refs = c->medium_refs.as<int>();
+    d.perlin_vec = c->perlin_vec.as<float4>();
+    d.perlin_perm = c->perlin_perm.as<int>();
 
     rl_scene_info& si = c->info;
     si = rl_scene_info{};

@@ -125,6 +125,21 @@ struct Flattener {
     std::string* err;
     int rc = RL_OK;
     int csg_depth = 0;
+    // while lowering the boundary of a ConstantMedium, leaves go to medium_refs instead of the LBVH input
+    bool in_boundary = false;
+    double blo[3], bhi[3];
+
+    void emit(const double lo[3], const double hi[3], int ref, int node) {
+        if (in_boundary) {
+            fs->medium_refs.push_back(ref);
+            for (int k = 0; k < 3; k++) {
+                blo[k] = std::fmin(blo[k], lo[k]);
+                bhi[k] = std::fmax(bhi[k], hi[k]);
+            }
+        } else {
+            push_aabb(fs, lo, hi, ref, node);
+        }
+    }
 
     bool fail(int code, const std::string& msg) {
         if (rc == RL_OK) {
@@ -159,6 +174,10 @@ struct Flattener {
                 return fail(RL_E_INVALID, "checker sub-texture out of range");
             if (t.kind == RL_TEX_OW_IMAGE && (t.image < 0 || t.image >= d->n_images))
                 return fail(RL_E_INVALID, "image index out of range");
+            if (t.kind == RL_TEX_OW_NOISE) {  // texture.rs:84-94: b.w = scale, idx.z = Perlin table
+                if (t.image < 0 || t.image >= d->n_perlins) return fail(RL_E_INVALID, "perlin index out of range");
+                o.b.w = (float)t.scale;
+            }
             fs->textures.push_back(o);
         }
         for (int i = 0; i < d->n_images; i++) {
@@ -171,6 +190,14 @@ struct Flattener {
             for (size_t k = 0; k < o.texels.size(); k++)
                 o.texels[k] = make_float4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 0.0f);
             fs->images.push_back(std::move(o));
+        }
+        for (int i = 0; i < d->n_perlins; i++) {  // perlin.rs:9-14
+            const rl_perlin& pn = d->perlins[i];
+            for (int k = 0; k < 256; k++)
+                fs->perlin_vec.push_back(make_float4((float)pn.randvec[k][0], (float)pn.randvec[k][1], (float)pn.randvec[k][2], 0.0f));
+            for (int k = 0; k < 256; k++) fs->perlin_perm.push_back(pn.perm_x[k] & 255);
+            for (int k = 0; k < 256; k++) fs->perlin_perm.push_back(pn.perm_y[k] & 255);
+            for (int k = 0; k < 256; k++) fs->perlin_perm.push_back(pn.perm_z[k] & 255);
         }
         for (int i = 0; i < d->n_materials; i++) {
             const rl_material& m = d->materials[i];
@@ -185,7 +212,7 @@ struct Flattener {
             } else {
                 o.a = make_float4((float)m.fuzz, (float)m.refractive_index, 0.0f, 0.0f);
                 o.b = make_float4(0.0f, 0.0f, 0.0f, as_f(m.kind));
-                if ((m.kind == RL_MAT_OW_LAMBERTIAN || m.kind == RL_MAT_OW_DIFFUSE_LIGHT) && m.texture < 0)
+                if ((m.kind == RL_MAT_OW_LAMBERTIAN || m.kind == RL_MAT_OW_DIFFUSE_LIGHT || m.kind == RL_MAT_OW_ISOTROPIC) && m.texture < 0)
                     return fail(RL_E_INVALID, "OW material without a texture");
             }
             fs->materials.push_back(o);
@@ -358,7 +385,7 @@ struct Flattener {
             lo[k] = std::fmin(a, std::fmin(b, c));
             hi[k] = std::fmax(a, std::fmax(b, c));
         }
-        push_aabb(fs, lo, hi, make_ref(REF_TRI, idx), node);
+        emit(lo, hi, make_ref(REF_TRI, idx), node);
     }
 
     // ---- OW ------------------------------------------------------------------------------------
@@ -397,10 +424,10 @@ struct Flattener {
                     lo[k] = std::fmin(a, b) - ar;
                     hi[k] = std::fmax(a, b) + ar;
                 }
-                if (ar >= (double)OW_BIG_RADIUS && (int)fs->big_refs.size() < OW_MAX_BIG)
+                if (!in_boundary && ar >= (double)OW_BIG_RADIUS && (int)fs->big_refs.size() < OW_MAX_BIG)
                     fs->big_refs.push_back(make_ref(REF_SPHERE, idx));  // tested once per ray, outside the LBVH
                 else
-                    push_aabb(fs, lo, hi, make_ref(REF_SPHERE, idx), id);
+                    emit(lo, hi, make_ref(REF_SPHERE, idx), id);
                 return true;
             }
             case RL_OW_QUAD: {
@@ -436,7 +463,7 @@ struct Flattener {
                     lo[k] = std::fmin(std::fmin(c[0], c[1]), std::fmin(c[2], c[3]));
                     hi[k] = std::fmax(std::fmax(c[0], c[1]), std::fmax(c[2], c[3]));
                 }
-                push_aabb(fs, lo, hi, make_ref(REF_QUAD, idx), id);
+                emit(lo, hi, make_ref(REF_QUAD, idx), id);
                 return true;
             }
             case RL_OW_TRIANGLE: {
@@ -486,6 +513,29 @@ struct Flattener {
                     return fail(RL_E_INVALID, "Cannot make a BVH node without hittables.");
                 for (int k = nd.child_begin; k < nd.child_end; k++)
                     if (!ow_node(d->children[k], fwd, inv, rotated, depth + 1)) return false;
+                return true;
+            }
+            case RL_OW_CONSTANT_MEDIUM: {  // hittable/constant_medium.rs:14-22
+                if (!check_material(nd.material)) return false;
+                const double* q = params(nd, 1);
+                if (!q) return false;
+                if (in_boundary) return fail(RL_E_UNSUPPORTED, "a ConstantMedium inside the boundary of another one");
+                if (d->materials[nd.material].kind != RL_MAT_OW_ISOTROPIC)
+                    return fail(RL_E_UNSUPPORTED, "ConstantMedium is only intended to be used with Isotropic material");
+                OwMedium m;
+                m.ref_begin = (int)fs->medium_refs.size();
+                m.neg_inv_density = (float)(-1.0 / q[0]);
+                m.material = nd.material;
+                in_boundary = true;
+                for (int k = 0; k < 3; k++) { blo[k] = INFINITY; bhi[k] = -INFINITY; }
+                bool ok = ow_node(nd.child_begin, fwd, inv, rotated, depth + 1);
+                in_boundary = false;
+                if (!ok) return false;
+                m.ref_count = (int)fs->medium_refs.size() - m.ref_begin;
+                if (m.ref_count == 0) return fail(RL_E_INVALID, "ConstantMedium with an empty boundary");
+                int idx = (int)fs->media.size();
+                fs->media.push_back(m);
+                push_aabb(fs, blo, bhi, make_ref(REF_MEDIUM, idx), id);  // bounding_box = the boundary's (85-87)
                 return true;
             }
             default:

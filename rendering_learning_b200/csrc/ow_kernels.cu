@@ -51,7 +51,51 @@ __device__ __forceinline__ float3 unit_vector(float u1, float u2) {
     return f3(r * c, r * s, z);
 }
 
+// PRIMS: what the scene holds (bit 0 spheres, bit 1 triangles, bit 2 quads, bit 3 constant media, bit 4 Noise
+// textures).  The render kernel is instantiated for "spheres only", "no spheres", "every surface" and "everything", so
+// a sphere scene carries no triangle / quad / image / medium / Perlin code (smaller code, fewer registers, fewer
+// instruction-cache misses: ncu showed 8 % of issue slots lost to `no_instruction` on the one-size-fits-all build).
+constexpr int PRIMS_SPHERES = 1, PRIMS_TRIS = 2, PRIMS_QUADS = 4, PRIMS_MEDIA = 8, PRIMS_NOISE = 16;
+constexpr int PRIMS_ALL = 7, PRIMS_FULL = 31;
+
+// ---- Perlin noise (perlin.rs:39-115) ---------------------------------------------------------------------
+__device__ __forceinline__ float perlin_noise(const float4* __restrict__ vec, const int* __restrict__ perm, float3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; di++) {
+        int px = __ldg(perm + ((i + di) & 255));
+        float wi = di ? uu : 1.0f - uu;
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++) {
+            int py = __ldg(perm + 256 + ((j + dj) & 255));
+            float wj = dj ? vv : 1.0f - vv;
+#pragma unroll
+            for (int dk = 0; dk < 2; dk++) {
+                int pz = __ldg(perm + 512 + ((k + dk) & 255));
+                float wk = dk ? ww : 1.0f - ww;
+                float4 c = __ldg(vec + (px ^ py ^ pz));
+                accum += wi * wj * wk * dot(f3(c), f3(u - (float)di, v - (float)dj, w - (float)dk));
+            }
+        }
+    }
+    return accum;
+}
+__device__ __forceinline__ float perlin_turb(const float4* vec, const int* perm, float3 p, int depth) {
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < depth; i++) {
+        accum = fmaf(weight, perlin_noise(vec, perm, p), accum);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(accum);
+}
+
 // ---- textures (texture.rs) -------------------------------------------------------------------------------
+template <int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ float3 tex_value(const DevScene& sc, int tex, float u, float v, float3 p) {
     DevTexture t = sc.textures[tex];
     for (int guard = 0; guard < 8 && __float_as_int(t.a.w) == RL_TEX_OW_CHECKER; guard++) {
@@ -71,6 +115,12 @@ __device__ __forceinline__ float3 tex_value(const DevScene& sc, int tex, float u
         float4 px = __ldg(im.texels + (size_t)j * im.width + i);
         return f3(px);
     }
+    if ((PRIMS & PRIMS_NOISE) && __float_as_int(t.a.w) == RL_TEX_OW_NOISE) {  // texture.rs:89-93
+        const float4* vec = sc.perlin_vec + 256 * t.idx.z;
+        const int* perm = sc.perlin_perm + 768 * t.idx.z;
+        float g = 0.5f * (1.0f + sinf(fmaf(t.b.w, p.z, 10.0f * perlin_turb(vec, perm, p, 7))));
+        return f3(g, g, g);
+    }
     return f3(t.a);
 }
 
@@ -82,16 +132,25 @@ struct OwHit {
 
 // One primitive test of world.hit: updates `h` when the primitive is hit closer than h.t.
 // `self_ref` is the primitive the ray starts on (never re-hit at t ~ 0; a sphere only at its far root).
-// PRIMS: which primitive kinds the scene holds (bit 0 spheres, bit 1 triangles, bit 2 quads).  The render kernel is
-// instantiated for "spheres only" and "everything", so a sphere scene carries no triangle / quad / image code (smaller
-// code, fewer registers, fewer instruction-cache misses: ncu showed 8 % of issue slots lost to `no_instruction`).
-constexpr int PRIMS_SPHERES = 1, PRIMS_TRIS = 2, PRIMS_QUADS = 4, PRIMS_ALL = 7;
+
+__device__ __forceinline__ unsigned hash32(unsigned x) {  // lowbias32 (Wellons): decorrelates the per-medium draws
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+template <bool COUNT, int PRIMS>
+__device__ __forceinline__ void ow_medium_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
+                                               float tmin, unsigned ray_rnd, OwHit& h, LocalCount<COUNT>& lc);
 
 template <bool COUNT, int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
-                                             int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc) {
+                                             int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc, unsigned ray_rnd = 0u) {
     const float3 o = pre.o, d = pre.d;
     int type = ref_type(ref), idx = ref_index(ref);
+    if ((PRIMS & PRIMS_MEDIA) && type == REF_MEDIUM) {
+        ow_medium_test<COUNT, PRIMS>(sc, ref, pre, a_dd, time, tmin, ray_rnd, h, lc);
+        return;
+    }
     if (PRIMS == PRIMS_SPHERES || ((PRIMS & PRIMS_SPHERES) && type == REF_SPHERE)) {  // sphere.rs:34-75
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
         if (COUNT) lc.prims++;
@@ -151,7 +210,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             return;
         }
         return;
-    } else if (PRIMS & PRIMS_QUADS) {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
+    } else if ((PRIMS & PRIMS_QUADS) && type == REF_QUAD) {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
         if (ref == self_ref) return;
         const OwQuad& qd = sc.quads[idx];
         float4 n4 = qd.n;
@@ -173,6 +232,45 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
     }
 }
 
+// ConstantMedium::hit (constant_medium.rs:28-83).  The boundary is a short list of ordinary primitives that are in
+// neither the LBVH nor the big list; entry and exit are two closest-hit passes over it (`boundary.hit(r, universe)`
+// and `boundary.hit(r, [t1 + 1e-4, inf))`).  The scattering distance is drawn from the ray's own counter-based draw
+// (`ray_rnd`, hashed with the medium index) — seeded, where the reference uses the process-global RNG.
+template <bool COUNT, int PRIMS>
+__device__ __forceinline__ void ow_medium_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
+                                               float tmin, unsigned ray_rnd, OwHit& h, LocalCount<COUNT>& lc) {
+    const OwMedium m = sc.media[ref_index(ref)];
+    constexpr int SURF = PRIMS & ~PRIMS_MEDIA;
+    float t1 = RL_INF, t2 = RL_INF;
+    for (int k = 0; k < m.ref_count; k++) {
+        OwHit b;
+        b.t = RL_INF; b.ref = -1; b.b1 = b.b2 = 0.0f;
+        ow_leaf_test<COUNT, SURF>(sc, sc.medium_refs[m.ref_begin + k], pre, a_dd, time, -1, -RL_INF, b, lc);
+        t1 = fminf(t1, b.t);
+    }
+    if (!(t1 < RL_INF)) return;
+    const float lo2 = t1 + fmaxf(1e-4f, 1e-6f * fabsf(t1));  // the reference's 1e-4, kept above the f32 ulp of t1
+    for (int k = 0; k < m.ref_count; k++) {
+        OwHit b;
+        b.t = RL_INF; b.ref = -1; b.b1 = b.b2 = 0.0f;
+        ow_leaf_test<COUNT, SURF>(sc, sc.medium_refs[m.ref_begin + k], pre, a_dd, time, -1, lo2, b, lc);
+        t2 = fminf(t2, b.t);
+    }
+    if (!(t2 < RL_INF)) return;
+    t1 = fmaxf(t1, tmin);
+    t2 = fminf(t2, h.t);
+    if (t1 >= t2) return;
+    t1 = fmaxf(t1, 0.0f);
+    const float ray_length = sqrtf(a_dd);
+    const float inside = (t2 - t1) * ray_length;
+    const float u = u01(hash32(ray_rnd ^ (0x9E3779B9u * (unsigned)(ref_index(ref) + 1))));
+    const float hit_distance = m.neg_inv_density * logf(u);  // u = 0: +inf, no scatter
+    if (hit_distance > inside) return;
+    h.t = t1 + hit_distance / ray_length;
+    h.ref = ref;
+    h.b1 = h.b2 = 0.0f;
+}
+
 // same test from (o, d) plus the watertight shear constants the v5 kernel computes once per ray (make_pre per triangle
 // test was 15 % of the Cornell-box warp instructions, at 4-6 lanes: profiles/r01_ncu_k_ow_render_v5_c5.json)
 struct TriShear {
@@ -188,7 +286,7 @@ __device__ __forceinline__ TriShear make_shear(float3 o, float3 d) {
 }
 template <bool COUNT, int PRIMS>
 __device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, float3 o, float3 d, const TriShear& sh, float time,
-                                                int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc) {
+                                                int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc, unsigned ray_rnd = 0u) {
     RayPre pre;
     pre.o = o;
     pre.d = d;
@@ -196,7 +294,7 @@ __device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, flo
         pre.kx = sh.k & 3; pre.ky = (sh.k >> 2) & 3; pre.kz = (sh.k >> 4) & 3;
         pre.Sx = sh.Sx; pre.Sy = sh.Sy; pre.Sz = sh.Sz;
     }
-    ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, dot(d, d), time, self_ref, tmin, h, lc);
+    ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, dot(d, d), time, self_ref, tmin, h, lc, ray_rnd);
 }
 
 // world.hit(r, [tmin, inf)) through the LBVH (callback form; used by rl_trace_batch and the v1 kernel).
@@ -266,7 +364,14 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
     int mat_id = 0;
     bool uv_from_sphere = false;
     float3 outward = f3(0.0f, 1.0f, 0.0f);
-    if (PRIMS == PRIMS_SPHERES || ((PRIMS & PRIMS_SPHERES) && type == REF_SPHERE)) {
+    bool in_medium = false;
+    if ((PRIMS & PRIMS_MEDIA) && type == REF_MEDIUM) {  // constant_medium.rs:68-75: p = r.at(t), the rest is arbitrary
+        pos = fma3(p.d, h.t, p.o);
+        outward = f3(1.0f, 0.0f, 0.0f);
+        u = v = 0.0f;
+        mat_id = sc.media[idx].material;
+        in_medium = true;
+    } else if (PRIMS == PRIMS_SPHERES || ((PRIMS & PRIMS_SPHERES) && type == REF_SPHERE)) {
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
         float3 center = fma3(f3(dc), p.time, f3(c));
         float3 q = fma3(p.d, h.t, p.o) - center;
@@ -288,14 +393,14 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
             v = s1.w * b0 + s3.x * h.b1 + s3.z * h.b2;
         }
         mat_id = __float_as_int(p0.w);
-    } else if (PRIMS & PRIMS_QUADS) {
+    } else if ((PRIMS & PRIMS_QUADS) && type == REF_QUAD) {
         const OwQuad& qd = sc.quads[idx];
         outward = f3(qd.n);
         float3 ip = fma3(p.d, h.t, p.o);
         pos = ip - outward * (dot(outward, ip) - qd.n.w);  // snapped onto the plane
         mat_id = qd.m.x;
     }
-    bool front = dot(p.d, outward) <= 0.0f;  // hittable/mod.rs:32-38
+    bool front = in_medium || dot(p.d, outward) <= 0.0f;  // hittable/mod.rs:32-38 (a medium hit is Face::Front)
     normal = front ? outward : -outward;
     const DevMaterial m = sc.materials[mat_id];
     int kind = __float_as_int(m.b.w);
@@ -307,7 +412,7 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
         v = theta * (1.0f / 3.14159265358979f);
     }
     if (kind == RL_MAT_OW_DIFFUSE_LIGHT) {  // material.rs:178-195
-        rad = p.thr * tex_value(sc, tex, u, v, pos);
+        rad = p.thr * tex_value<PRIMS>(sc, tex, u, v, pos);
         return false;
     }
     float3 dir;
@@ -315,10 +420,13 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
     // Lambertian and Metal both draw a UnitSphere sample (Metal even with fuzz = 0, material.rs:113): evaluated once,
     // before the material branches, so the warp runs it converged
     const float3 uvec = kind == RL_MAT_OW_DIELECTRIC ? f3(0.0f, 0.0f, 0.0f) : unit_vector(u01(rnd.x), u01(rnd.y));
-    if (kind == RL_MAT_OW_LAMBERTIAN) {  // material.rs:74-92
+    if ((PRIMS & PRIMS_MEDIA) && kind == RL_MAT_OW_ISOTROPIC) {  // material.rs:201-216
+        dir = uvec;
+        atten = tex_value<PRIMS>(sc, tex, u, v, pos);
+    } else if (kind == RL_MAT_OW_LAMBERTIAN) {  // material.rs:74-92
         dir = normal + uvec;
         if (fabsf(dir.x) <= 1e-8f && fabsf(dir.y) <= 1e-8f && fabsf(dir.z) <= 1e-8f) dir = normal;
-        atten = tex_value(sc, tex, u, v, pos);
+        atten = tex_value<PRIMS>(sc, tex, u, v, pos);
     } else if (kind == RL_MAT_OW_METAL) {  // material.rs:105-122
         float3 refl = p.d - normal * (2.0f * dot(p.d, normal));
         dir = fma3(uvec, m.a.x, normalize(refl));
@@ -527,6 +635,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     float tmin = 0.0f;
     TriShear shear;
     shear.k = 0; shear.Sx = shear.Sy = shear.Sz = 0.0f;
+    unsigned ray_rnd = 0u;  // the ray's draw for ConstantMedium scattering distances
     OwHit hit;
     hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
     // queue (warp-uniform, one slot per warp in shared memory): the current reserved batch [next, end) and the base of
@@ -641,11 +750,13 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             oi = p.o * inv_d;
             tmin = ow_tmin(p);
             if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
+            if (PRIMS & PRIMS_MEDIA)
+                ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
             sp = 0;
             if (COUNT) lc.rays++;
             for (int k = 0; k < sc.n_big; k++)  // the big list: once per ray, here, with the serviced lanes
-                ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc);
+                ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc, ray_rnd);
             node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
         }
         const unsigned m_done = __ballot_sync(FULL, done);
@@ -684,7 +795,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
         while (true) {
             // leaf round: every lane parked at a leaf tests it and pops
             if (node < 0 && node != TRAV_END) {
-                ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc);
+                ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc, ray_rnd);
                 node = sp > 0 ? stack_node[--sp] : TRAV_END;
             }
             const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));
@@ -840,15 +951,18 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
     K3 k3 = nullptr;
     K5 k4 = nullptr;
-    const bool spheres_only = !generic && sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0;
-    const bool no_spheres = !generic && sc.n_spheres == 0;
+    const bool extras = sc.n_media > 0 || sc.n_perlins > 0;  // constant media / Noise textures: the FULL build
+    const bool spheres_only = !generic && !extras && sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0;
+    const bool no_spheres = !generic && !extras && sc.n_spheres == 0;
     // measured (profiles/r01_sweep_ow_v5.log and the C5 runs after it): the spheres-only and the no-spheres builds fit
     // 64 registers (4 CTAs/SM) with 18 / 86 B of spills and win there (C5 @64 spp: 66.7 vs 69.4 ms); the build that
     // carries every primitive kind is better at 80 registers (3 CTAs/SM)
     const int minb = minb_env ? minb_env : ((spheres_only || no_spheres) ? 4 : 3);
     constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
-    if (variant == 3) {
+    if (variant == 3 && !extras) {  // v3 predates media / Noise
         k3 = instrumented ? (K3)k_ow_render<true, 1, 4> : (K3)k_ow_render<false, 1, 4>;
+    } else if (extras) {
+        k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FULL> : (K5)k_ow_render5<false, 3, PRIMS_FULL>;
     } else if (spheres_only) {
         if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_SPHERES> : (K5)k_ow_render5<false, 4, PRIMS_SPHERES>;
         else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_SPHERES> : (K5)k_ow_render5<false, 3, PRIMS_SPHERES>;

@@ -19,7 +19,7 @@ enum : int {
 };
 
 // BVH leaf reference: (type << 28) | index into the per-type array
-constexpr int REF_TRI = 0, REF_SPHERE = 1, REF_QUAD = 2;
+constexpr int REF_TRI = 0, REF_SPHERE = 1, REF_QUAD = 2, REF_MEDIUM = 3;
 __host__ __device__ inline int make_ref(int type, int index) { return (type << 28) | index; }
 __host__ __device__ inline int ref_type(int ref) { return (ref >> 28) & 7; }
 __host__ __device__ inline int ref_index(int ref) { return ref & 0x0FFFFFFF; }
@@ -67,6 +67,12 @@ struct OwQuad {  // 64 B; the intersection test reads the first 48
     float4 b;  // beta  = b.xyz . p - b.w, with b.xyz = w x u and b.w = b.xyz . q
     int4 m;    // x = material
 };
+struct OwMedium {  // 16 B — hittable/constant_medium.rs:8-12
+    int ref_begin, ref_count;  // boundary primitives: medium_refs[ref_begin .. +ref_count) (never in the LBVH themselves)
+    float neg_inv_density;
+    int material;              // the phase function (Isotropic)
+};
+
 struct DevMaterial {  // 48 B
     float4 color;  // rgb (RTC surface colour / OW metal albedo), w = texture index (int bits, -1 none)
     float4 a;      // RTC: ambient, diffuse, specular, shininess | OW: fuzz, refractive_index, 0, 0
@@ -101,6 +107,7 @@ struct DevScene {
     int n_bvh_prims, n_bvh_nodes;  // traversal nodes (>= 1 when n_bvh_prims >= 1)
     int n_big;                     // OW: leaf refs tested brute force before the traversal
     int n_csg;                     // RTC: CSG nodes
+    int n_media, n_perlins;        // OW: constant media, Perlin tables
     int n_materials, n_textures, n_lights, n_images, n_xforms;
     int has_transparency;
     int max_reflection_depth;
@@ -119,6 +126,10 @@ struct DevScene {
     const DevLight* lights;
     const BvhNode* nodes;
     const int* big_refs;
+    const OwMedium* media;
+    const int* medium_refs;
+    const float4* perlin_vec;  // [n_perlins][256] gradient vectors
+    const int* perlin_perm;    // [n_perlins][3][256] perm_x, perm_y, perm_z
     const int4* csg;  // (operation, lo, mid, hi): left child = prims [lo, mid), right child = prims [mid, hi)
 };
 
@@ -143,6 +154,10 @@ struct FlatScene {
     std::vector<int> bvh_node_id;  // [n]
     std::vector<int> big_refs;     // OW leaf refs kept out of the LBVH (OW_BIG_RADIUS)
     std::vector<int4> csg;         // RTC CSG nodes, post-order
+    std::vector<OwMedium> media;
+    std::vector<int> medium_refs;
+    std::vector<float4> perlin_vec;
+    std::vector<int> perlin_perm;
     int has_transparency = 0;
     int max_reflection_depth = 5;
     float void_color[3] = {0, 0, 0};

@@ -24,6 +24,7 @@ class SceneDesc:
         self.textures: list[A.rl_texture] = []
         self.images: list[np.ndarray] = []
         self.lights: list[A.rl_light] = []
+        self.perlins: list[A.rl_perlin] = []
         self.max_reflection_depth = 5
         self.void_color = (0.0, 0.0, 0.0)
         self._mat_ids: dict[int, int] = {}
@@ -74,6 +75,15 @@ class SceneDesc:
         self.images.append(arr)
         return len(self.images) - 1
 
+    def add_perlin(self, randvec, perm_x, perm_y, perm_z) -> int:
+        p = A.rl_perlin()
+        for i in range(256):
+            for k in range(3):
+                p.randvec[i][k] = float(randvec[i][k])
+            p.perm_x[i], p.perm_y[i], p.perm_z[i] = int(perm_x[i]), int(perm_y[i]), int(perm_z[i])
+        self.perlins.append(p)
+        return len(self.perlins) - 1
+
     # ---- freezing --------------------------------------------------------------------------
     def freeze(self) -> A.rl_scene_desc:
         if self._frozen is not None:
@@ -112,6 +122,9 @@ class SceneDesc:
         self._lights_arr = (A.rl_light * max(len(self.lights), 1))(*self.lights)
         d.lights = C.cast(self._lights_arr, C.POINTER(A.rl_light))
         d.n_lights = len(self.lights)
+        self._perlin_arr = (A.rl_perlin * max(len(self.perlins), 1))(*self.perlins)
+        d.perlins = C.cast(self._perlin_arr, C.POINTER(A.rl_perlin))
+        d.n_perlins = len(self.perlins)
         d.max_reflection_depth = int(self.max_reflection_depth)
         d.void_color = (C.c_double * 3)(*self.void_color)
         self._frozen = d
@@ -125,4 +138,5 @@ class SceneDesc:
         n += C.sizeof(A.rl_texture) * len(self.textures)
         n += C.sizeof(A.rl_light) * len(self.lights)
         n += sum(im.nbytes for im in self.images)
+        n += C.sizeof(A.rl_perlin) * len(self.perlins)
         return n

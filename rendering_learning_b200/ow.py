@@ -93,6 +93,73 @@ class Image(Texture):
         return sd.texture_id(self, make)
 
 
+class Perlin:
+    """perlin.rs:9-36 — the tables `Perlin::new(rng)` draws: 256 unit vectors, then three permutations.
+    `rng` offers `unit_sphere()` (rand_distr::UnitSphere, vec3.rs:72-75) and `gen_range_usize(n)`
+    (`rng.gen_range(0..n)`, perlin.rs:84); `scenes.Xoshiro256PlusPlus` is the generator the reference's examples use."""
+
+    def __init__(self, randvec, perm_x, perm_y, perm_z):
+        self.randvec, self.perm_x, self.perm_y, self.perm_z = randvec, perm_x, perm_y, perm_z
+
+    @classmethod
+    def new(cls, rng):
+        randvec = [rng.unit_sphere() for _ in range(256)]
+
+        def permutation():  # permute (perlin.rs:81-89): target drawn from 0..i, EXCLUSIVE of i
+            p = list(range(256))
+            for i in range(255, 0, -1):
+                t = rng.gen_range_usize(i)
+                p[i], p[t] = p[t], p[i]
+            return p
+        return cls(randvec, permutation(), permutation(), permutation())
+
+    def noise(self, p) -> float:
+        """perlin.rs:39-63 + perlin_interp 91-115 (host restatement, used by tests)"""
+        import math
+        fl = [math.floor(c) for c in p]
+        u, v, w = (p[0] - fl[0], p[1] - fl[1], p[2] - fl[2])
+        i, j, k = int(fl[0]), int(fl[1]), int(fl[2])
+        uu, vv, ww = u * u * (3.0 - 2.0 * u), v * v * (3.0 - 2.0 * v), w * w * (3.0 - 2.0 * w)
+        acc = 0.0
+        for di in range(2):
+            for dj in range(2):
+                for dk in range(2):
+                    c = self.randvec[self.perm_x[(i + di) & 255] ^ self.perm_y[(j + dj) & 255] ^ self.perm_z[(k + dk) & 255]]
+                    wv = (u - di, v - dj, w - dk)
+                    acc += ((di * uu + (1.0 - di) * (1.0 - uu)) * (dj * vv + (1.0 - dj) * (1.0 - vv)) *
+                            (dk * ww + (1.0 - dk) * (1.0 - ww)) * (c[0] * wv[0] + c[1] * wv[1] + c[2] * wv[2]))
+        return acc
+
+    def turb(self, p, depth: int) -> float:
+        """perlin.rs:65-78"""
+        acc, weight, q = 0.0, 1.0, tuple(p)
+        for _ in range(depth):
+            acc += weight * self.noise(q)
+            weight *= 0.5
+            q = (q[0] * 2.0, q[1] * 2.0, q[2] * 2.0)
+        return abs(acc)
+
+
+@dataclass(eq=False)
+class Noise(Texture):
+    """texture.rs:84-94"""
+    noise: Perlin
+    scale: float
+
+    def value(self, u, v, p):
+        import math
+        g = 0.5 * (1.0 + math.sin(self.scale * p[2] + 10.0 * self.noise.turb(p, 7)))
+        return (g, g, g)
+
+    def _lower(self, sd):
+        def make():
+            t = _new_tex(A.RL_TEX_OW_NOISE)
+            t.image = sd.add_perlin(self.noise.randvec, self.noise.perm_x, self.noise.perm_y, self.noise.perm_z)
+            t.scale = float(self.scale)
+            return t
+        return sd.texture_id(self, make)
+
+
 # ---- materials (material.rs) --------------------------------------------------------------------
 
 
@@ -153,6 +220,19 @@ class DiffuseLight(Material):
     def _lower(self, sd):
         def make():
             m = _new_mat(A.RL_MAT_OW_DIFFUSE_LIGHT)
+            m.texture = self.texture._lower(sd)
+            return m
+        return sd.material_id(self, make)
+
+
+@dataclass(eq=False)
+class Isotropic(Material):
+    """material.rs:197-221 — the phase function of a ConstantMedium"""
+    texture: Texture
+
+    def _lower(self, sd):
+        def make():
+            m = _new_mat(A.RL_MAT_OW_ISOTROPIC)
             m.texture = self.texture._lower(sd)
             return m
         return sd.material_id(self, make)
@@ -326,6 +406,28 @@ class Translate(Hittable):
     def _lower(self, sd):
         me = sd.add_node(A.RL_OW_TRANSLATE, param=sd.add_params(self.offset))
         c = self.object._lower(sd)
+        sd.set_node_children(me, c, c + 1)
+        return me
+
+
+class ConstantMedium(Hittable):
+    """hittable/constant_medium.rs:8-23.  The reference draws the scattering distance from the process-global
+    RNG (its own TODO at 52-55: renders with a medium are not repeatable); the device path and the oracle draw it
+    from the path's seeded stream instead, so renders are deterministic — parity is statistical either way."""
+
+    def __init__(self, boundary: Hittable, density: float, material: Material):
+        self.boundary, self.density, self.phase_function = boundary, float(density), material
+        # f64 division as in Rust: a zero density gives -inf (the medium never scatters), not a panic
+        self.neg_inv_density = -1.0 / self.density if self.density != 0.0 else float("-inf")
+
+    @classmethod
+    def new(cls, boundary, density, material):
+        return cls(boundary, density, material)
+
+    def _lower(self, sd):
+        me = sd.add_node(A.RL_OW_CONSTANT_MEDIUM, material=self.phase_function._lower(sd),
+                         param=sd.add_params([self.density]))
+        c = self.boundary._lower(sd)
         sd.set_node_children(me, c, c + 1)
         return me
 

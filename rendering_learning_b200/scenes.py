@@ -254,6 +254,35 @@ class _Xoshiro256PlusPlus:
             if res < high:
                 return res
 
+    def uniform_m1_1(self) -> float:
+        """rand 0.8.5 `Uniform::<f64>::new(-1.0, 1.0)` as rand_distr samples it: 52-bit v in [0, 1), v * 2 - 1"""
+        import struct
+        bits = (self.next_u64() >> 12) | 0x3FF0000000000000
+        return (struct.unpack("<d", struct.pack("<Q", bits))[0] - 1.0) * 2.0 + -1.0
+
+    def unit_sphere(self):
+        """rand_distr 0.4.3 UnitSphere (Marsaglia 1972) — `Vec3::random_unit_vector` (vec3.rs:72-75)"""
+        import math
+        while True:
+            x1, x2 = self.uniform_m1_1(), self.uniform_m1_1()
+            s2 = x1 * x1 + x2 * x2
+            if s2 >= 1.0:
+                continue
+            f = 2.0 * math.sqrt(1.0 - s2)
+            return (x1 * f, x2 * f, 1.0 - 2.0 * s2)
+
+    def gen_range_usize(self, n: int) -> int:
+        """rand 0.8.5 `gen_range(0..n)` for usize: widening multiply + zone rejection"""
+        zone = ((n << (64 - n.bit_length())) - 1) & self.M
+        while True:
+            m = self.next_u64() * n
+            hi, lo = m >> 64, m & self.M
+            if lo <= zone:
+                return hi
+
+
+Xoshiro256PlusPlus = _Xoshiro256PlusPlus
+
 
 def ow_cover_world():
     """OW/examples/bouncing_spheres.rs:16-117 — the RTIOW cover scene (BASELINE config C4)."""
@@ -296,6 +325,53 @@ def ow_cover_params(image_width=1200, samples_per_pixel=500, max_depth=50, seed=
                            samples_per_pixel=samples_per_pixel, max_depth=max_depth, vfov=20.0,
                            lookfrom=ow.Point3(13.0, 2.0, 3.0), lookat=ow.Point3(0.0, 0.0, 0.0),
                            vup=ow.Vec3(0.0, 1.0, 0.0), defocus_angle=0.6, focus_dist=10.0, seed=seed)
+
+
+def ow_perlin_spheres():
+    """OW/examples/perlin_spheres.rs:14-57 — two spheres with the marble Noise texture"""
+    from . import ow
+    rng = _Xoshiro256PlusPlus(1)
+    mat = ow.Lambertian(ow.Noise(ow.Perlin.new(rng), 4.0))
+    world = [ow.Sphere(ow.Center.Stationary((0.0, -1000.0, 0.0)), 1000.0, mat),
+             ow.Sphere(ow.Center.Stationary((0.0, 2.0, 0.0)), 2.0, mat)]
+    params = ow.CameraParams(aspect_ratio=16.0 / 9.0, image_width=400, samples_per_pixel=100, max_depth=50, vfov=20.0,
+                             lookfrom=(13.0, 2.0, 3.0), lookat=(0.0, 0.0, 0.0), vup=(0.0, 1.0, 0.0), defocus_angle=0.0)
+    return world, params
+
+
+def _ow_box(a, b, material):
+    """examples/common/mod.rs make_box: the six quads of the axis-aligned box with opposite corners a, b"""
+    from . import ow
+    lo = tuple(min(x, y) for x, y in zip(a, b))
+    hi = tuple(max(x, y) for x, y in zip(a, b))
+    dx, dy, dz = (hi[0] - lo[0], 0.0, 0.0), (0.0, hi[1] - lo[1], 0.0), (0.0, 0.0, hi[2] - lo[2])
+    neg = lambda v: (-v[0], -v[1], -v[2])
+    return [ow.Quad.new((lo[0], lo[1], hi[2]), dx, dy, material), ow.Quad.new((hi[0], lo[1], hi[2]), neg(dz), dy, material),
+            ow.Quad.new((hi[0], lo[1], lo[2]), neg(dx), dy, material), ow.Quad.new((lo[0], lo[1], lo[2]), dz, dy, material),
+            ow.Quad.new((lo[0], hi[1], hi[2]), dx, neg(dz), material), ow.Quad.new((lo[0], lo[1], lo[2]), dx, dz, material)]
+
+
+def ow_cornell_smoke():
+    """OW/examples/cornell_smoke.rs — Cornell box with two boxes of smoke (ConstantMedium + Isotropic)"""
+    from . import ow
+    red = ow.Lambertian(ow.SolidColor((0.65, 0.05, 0.05)))
+    white = ow.Lambertian(ow.SolidColor((0.73, 0.73, 0.73)))
+    green = ow.Lambertian(ow.SolidColor((0.12, 0.45, 0.15)))
+    light = ow.DiffuseLight(ow.SolidColor((7.0, 7.0, 7.0)))
+    world = [ow.Quad.new((555.0, 0.0, 0.0), (0.0, 555.0, 0.0), (0.0, 0.0, 555.0), green),
+             ow.Quad.new((0.0, 0.0, 0.0), (0.0, 555.0, 0.0), (0.0, 0.0, 555.0), red),
+             ow.Quad.new((113.0, 554.0, 127.0), (330.0, 0.0, 0.0), (0.0, 0.0, 305.0), light),
+             ow.Quad.new((0.0, 555.0, 0.0), (555.0, 0.0, 0.0), (0.0, 0.0, 555.0), white),
+             ow.Quad.new((0.0, 0.0, 0.0), (555.0, 0.0, 0.0), (0.0, 0.0, 555.0), white),
+             ow.Quad.new((0.0, 0.0, 555.0), (555.0, 0.0, 0.0), (0.0, 555.0, 0.0), white)]
+    box1 = ow.HittableList(_ow_box((0.0, 0.0, 0.0), (165.0, 330.0, 165.0), white)).rotate_y(15.0).translate((265.0, 0.0, 295.0))
+    box2 = ow.HittableList(_ow_box((0.0, 0.0, 0.0), (165.0, 165.0, 165.0), white)).rotate_y(-18.0).translate((130.0, 0.0, 65.0))
+    world.append(ow.ConstantMedium.new(box1, 0.01, ow.Isotropic(ow.SolidColor((0.0, 0.0, 0.0)))))
+    world.append(ow.ConstantMedium.new(box2, 0.01, ow.Isotropic(ow.SolidColor((1.0, 1.0, 1.0)))))
+    params = ow.CameraParams(aspect_ratio=1.0, image_width=600, samples_per_pixel=200, max_depth=50, vfov=40.0,
+                             lookfrom=(278.0, 278.0, -800.0), lookat=(278.0, 278.0, 0.0), vup=(0.0, 1.0, 0.0),
+                             defocus_angle=0.0, background=(0.0, 0.0, 0.0))
+    return world, params
 
 
 def ow_spot_texture() -> np.ndarray:

@@ -50,9 +50,27 @@ impl Image {
     }
 }
 
+impl crate::texture::Noise {
+    /// Perlin { randvec, perm_x, perm_y, perm_z } (perlin.rs:9-14) are private: read them through a `pub(crate)` view
+    pub fn lower(&self, out: &mut SceneBuilder) -> i32 {
+        out.texture_id(self, |out| {
+            let mut p = sys::rl_perlin { randvec: [[0.0; 3]; 256], perm_x: [0; 256], perm_y: [0; 256], perm_z: [0; 256] };
+            for i in 0..256 {
+                p.randvec[i] = v3(&self.noise.randvec[i]);
+                p.perm_x[i] = self.noise.perm_x[i] as i32;
+                p.perm_y[i] = self.noise.perm_y[i] as i32;
+                p.perm_z[i] = self.noise.perm_z[i] as i32;
+            }
+            let id = out.add_perlin(p);
+            sys::rl_texture { image: id, scale: self.scale, ..tex(sys::RL_TEX_OW_NOISE) }
+        })
+    }
+}
+
 // ---- materials (material.rs) ----------------------------------------------------------------------------------------
 impl<T: Texture> Lambertian<T>   { pub fn lower(&self, out: &mut SceneBuilder) -> i32 { out.material_id(self, |out| sys::rl_material { texture: self.texture.lower(out), ..mat(sys::RL_MAT_OW_LAMBERTIAN) }) } }
 impl<T: Texture> DiffuseLight<T> { pub fn lower(&self, out: &mut SceneBuilder) -> i32 { out.material_id(self, |out| sys::rl_material { texture: self.texture.lower(out), ..mat(sys::RL_MAT_OW_DIFFUSE_LIGHT) }) } }
+impl<T: Texture> crate::material::Isotropic<T> { pub fn lower(&self, out: &mut SceneBuilder) -> i32 { out.material_id(self, |out| sys::rl_material { texture: self.texture.lower(out), ..mat(sys::RL_MAT_OW_ISOTROPIC) }) } }
 impl Metal      { pub fn lower(&self, out: &mut SceneBuilder) -> i32 { out.material_id(self, |_| sys::rl_material { color: v3(&self.albedo), fuzz: self.fuzz, ..mat(sys::RL_MAT_OW_METAL) }) } }
 impl Dielectric { pub fn lower(&self, out: &mut SceneBuilder) -> i32 { out.material_id(self, |_| sys::rl_material { refractive_index: self.refraction_index, ..mat(sys::RL_MAT_OW_DIELECTRIC) }) } }
 
@@ -105,6 +123,17 @@ impl<H: Hittable + LowerOw> LowerOw for Translate<H> {
         let p = out.add_params(&v3(&self.offset));
         let me = out.add_node(sys::RL_OW_TRANSLATE, -1, 0, p);
         let c = self.object.lower(out);
+        out.set_node_children(me, c, c + 1);
+        me
+    }
+}
+impl<M: Material, H: Hittable + LowerOw> LowerOw for crate::hittable::constant_medium::ConstantMedium<M, H> {
+    /// fields boundary / neg_inv_density / phase_function are private (constant_medium.rs:8-12)
+    fn lower(&self, out: &mut SceneBuilder) -> i32 {
+        let m = self.phase_function.lower(out);
+        let p = out.add_params(&[-1.0 / self.neg_inv_density]); // density
+        let me = out.add_node(sys::RL_OW_CONSTANT_MEDIUM, m, 0, p);
+        let c = self.boundary.lower(out);
         out.set_node_children(me, c, c + 1);
         me
     }

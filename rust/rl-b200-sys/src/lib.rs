@@ -1,11 +1,11 @@
 //! `extern "C"` surface of `librl_b200.so` — a field-for-field transcription of `include/rl_b200.h`
-//! (ABI version 1).  `tests/test_abi.py::test_rust_sys_matches_header` keeps this file and the header in
+//! (ABI version 2).  `tests/test_abi.py::test_rust_sys_matches_header` keeps this file and the header in
 //! step.  Nothing here is safe; the safe wrapper is the `rl-b200` crate.
 #![allow(non_camel_case_types)]
 
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RL_B200_ABI_VERSION: i32 = 1;
+pub const RL_B200_ABI_VERSION: i32 = 2;
 
 pub const RL_OK: c_int = 0;
 pub const RL_E_INVALID: c_int = -1;
@@ -35,6 +35,7 @@ pub const RL_OW_TRANSFORM: i32 = 35;
 pub const RL_OW_TRANSLATE: i32 = 36;
 pub const RL_OW_BVH: i32 = 37;
 pub const RL_OW_LIST: i32 = 38;
+pub const RL_OW_CONSTANT_MEDIUM: i32 = 39;
 
 pub const RL_CSG_UNION: i32 = 0;
 pub const RL_CSG_INTERSECTION: i32 = 1;
@@ -45,6 +46,7 @@ pub const RL_MAT_OW_LAMBERTIAN: i32 = 16;
 pub const RL_MAT_OW_METAL: i32 = 17;
 pub const RL_MAT_OW_DIELECTRIC: i32 = 18;
 pub const RL_MAT_OW_DIFFUSE_LIGHT: i32 = 19;
+pub const RL_MAT_OW_ISOTROPIC: i32 = 20;
 
 pub const RL_TEX_RTC_STRIPE: i32 = 1;
 pub const RL_TEX_RTC_CHECKER3D: i32 = 2;
@@ -53,6 +55,7 @@ pub const RL_TEX_RTC_RING: i32 = 4;
 pub const RL_TEX_OW_SOLID: i32 = 16;
 pub const RL_TEX_OW_CHECKER: i32 = 17;
 pub const RL_TEX_OW_IMAGE: i32 = 18;
+pub const RL_TEX_OW_NOISE: i32 = 19;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -103,6 +106,15 @@ pub struct rl_image {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct rl_perlin {
+    pub randvec: [[f64; 3]; 256],
+    pub perm_x: [i32; 256],
+    pub perm_y: [i32; 256],
+    pub perm_z: [i32; 256],
+}
+
+#[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct rl_light {
     pub position: [f64; 3],
@@ -132,6 +144,8 @@ pub struct rl_scene_desc {
     pub n_lights: i32,
     pub max_reflection_depth: i32,
     pub void_color: [f64; 3],
+    pub perlins: *const rl_perlin,
+    pub n_perlins: i32,
 }
 
 #[repr(C)]

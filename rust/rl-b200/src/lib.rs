@@ -94,6 +94,8 @@ impl Ctx {
             n_lights: scene.lights.len() as i32,
             max_reflection_depth: scene.max_reflection_depth,
             void_color: scene.void_color,
+            perlins: scene.perlins.as_ptr(),
+            n_perlins: scene.perlins.len() as i32,
         };
         self.check(unsafe { sys::rl_scene_upload(self.raw, &d) })
     }
@@ -141,6 +143,7 @@ pub struct SceneBuilder {
     pub textures: Vec<sys::rl_texture>,
     pub images: Vec<(i32, i32, Vec<f32>)>,
     pub lights: Vec<sys::rl_light>,
+    pub perlins: Vec<sys::rl_perlin>,
     pub max_reflection_depth: i32,
     pub void_color: [f64; 3],
     // materials / textures are shared by ADDRESS, like `&Material` / `Box<dyn Material>` in the reference
@@ -160,6 +163,7 @@ impl SceneBuilder {
             textures: vec![],
             images: vec![],
             lights: vec![],
+            perlins: vec![],
             max_reflection_depth: 5,
             void_color: [0.0; 3],
             mat_ids: HashMap::new(),
@@ -212,6 +216,11 @@ impl SceneBuilder {
         let id = self.textures.len() as i32 - 1;
         self.tex_ids.insert(k, id);
         id
+    }
+
+    pub fn add_perlin(&mut self, p: sys::rl_perlin) -> i32 {
+        self.perlins.push(p);
+        self.perlins.len() as i32 - 1
     }
 
     pub fn add_image(&mut self, width: i32, height: i32, rgb: Vec<f32>) -> i32 {

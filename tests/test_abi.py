@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    structs = ["rl_node", "rl_material", "rl_texture", "rl_image", "rl_light", "rl_scene_desc",
+    structs = ["rl_node", "rl_material", "rl_texture", "rl_image", "rl_perlin", "rl_light", "rl_scene_desc",
                "rl_rtc_camera", "rl_ow_camera", "rl_ray", "rl_hit", "rl_stats", "rl_scene_info",
                "rl_lbvh_host", "rl_job"]
     prog = '#include <stdio.h>\n#include "rl_b200.h"\nint main(){' + "".join(
@@ -94,10 +94,13 @@ def _c_structs():
                 item = item.strip()
                 ptr = bool(ptr0) or item.startswith("*")
                 item = item.lstrip("* ")
-                am = re.match(r"(\w+)\[(\d+)\]", item)
+                am = re.match(r"(\w+)((?:\[\d+\])+)$", item)
                 base = _C2RUST.get(ctype, ctype)
                 if am:
-                    fields.append((am.group(1), f"[{base}; {am.group(2)}]"))
+                    ty = base
+                    for dim in reversed(re.findall(r"\[(\d+)\]", am.group(2))):  # C a[256][3] == Rust [[T; 3]; 256]
+                        ty = f"[{ty}; {dim}]"
+                    fields.append((am.group(1), ty))
                 elif ptr:
                     fields.append((item, ("*const " if const else "*mut ") + base))
                 else:

@@ -26,6 +26,19 @@ CASES = {
 }
 
 
+def _small(builder, width):
+    world, params = builder()
+    params.image_width = width
+    return world, params
+
+
+# Noise / Perlin texture, ConstantMedium + Isotropic (examples/perlin_spheres.rs, cornell_smoke.rs)
+EXTRA_CASES = {
+    "perlin_spheres": lambda: _small(scenes.ow_perlin_spheres, 200),
+    "cornell_smoke": lambda: _small(scenes.ow_cornell_smoke, 120),
+}
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_hit_ids_and_t_on_reference_camera_rays(ctx, oracle, name):
     world, params = CASES[name]()
@@ -67,6 +80,47 @@ def test_psnr_at_equal_spp(ctx, oracle, name):
     # unbiasedness: mean radiance agrees with the 8N-spp oracle render within 1.5 %
     m_gpu, m_hi = sums.mean() / spp, o_hi.mean() / (8 * spp)
     assert abs(m_gpu - m_hi) <= 0.015 * m_hi, (m_gpu, m_hi)
+
+
+@pytest.mark.parametrize("name", list(EXTRA_CASES))
+def test_psnr_noise_and_media(ctx, oracle, name):
+    """same protocol as test_psnr_at_equal_spp for the §8f.2 surface models"""
+    world, params = EXTRA_CASES[name]()
+    spp = 32
+    params.samples_per_pixel = spp
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    sums, st = ctx.render_ow(params.abi())
+    again, _ = ctx.render_ow(params.abi())
+    assert np.array_equal(sums, again)  # the medium's scattering draw is seeded: renders repeat bit for bit
+    h = sums.shape[0]
+    gpu = ow.Canvas(spp, params.image_width, h, sums).to_u8()
+    other = params.abi()
+    other.seed = 12345
+    o_other, _ = oracle.ow_render(desc, other)
+    hi = params.abi()
+    hi.seed = 777
+    hi.samples_per_pixel = 8 * spp
+    o_hi, _ = oracle.ow_render(desc, hi)
+    ref_hi = ow.Canvas(8 * spp, params.image_width, h, o_hi).to_u8()
+    cpu = ow.Canvas(spp, params.image_width, h, o_other).to_u8()
+    p_gpu, p_cpu = psnr(gpu, ref_hi), psnr(cpu, ref_hi)
+    assert p_gpu >= p_cpu - 0.5, (p_gpu, p_cpu)
+    m_gpu, m_hi = sums.mean() / spp, o_hi.mean() / (8 * spp)
+    assert abs(m_gpu - m_hi) <= 0.02 * m_hi, (m_gpu, m_hi)
+
+
+def test_medium_transmission_is_beer_lambert(ctx):
+    """a slab of density 1.5 and thickness 1 in front of a white background transmits exp(-1.5)"""
+    import math
+    black = ow.Isotropic(ow.SolidColor((0.0, 0.0, 0.0)))
+    wall = ow.Lambertian(ow.SolidColor((0.5, 0.5, 0.5)))
+    box = ow.HittableList(scenes._ow_box((-50.0, -50.0, -1.0), (50.0, 50.0, 0.0), wall))
+    params = ow.CameraParams(aspect_ratio=1.0, image_width=64, samples_per_pixel=256, max_depth=10, vfov=1.0,
+                             lookfrom=(0.0, 0.0, 5.0), lookat=(0.0, 0.0, 0.0), vup=(0.0, 1.0, 0.0),
+                             background=(1.0, 1.0, 1.0), seed=5)
+    cv = ow.Camera.new(params).render([ow.ConstantMedium.new(box, 1.5, black)], ctx=ctx)
+    assert abs(cv.pixel_data().mean() - math.exp(-1.5)) < 0.003
 
 
 def test_determinism_and_checkpoint_semantics(ctx):

@@ -122,3 +122,50 @@ def test_fixture_meshes_present():
     s = scenes.load_mesh("spot")
     assert s["tri_p"].shape == (5856, 3, 3) and s["has_uv"].all() and not s["has_n"].any()
     assert scenes.ow_spot_texture().shape == (1024, 1024, 3)
+
+
+def test_perlin_tables_and_noise(oracle):
+    """perlin.rs: the tables Perlin::new draws, and noise / turb / Noise::value — host mirror vs oracle restatement"""
+    world, _ = scenes.ow_perlin_spheres()
+    noise = world[0].material.texture
+    pn = noise.noise
+    assert len(pn.randvec) == 256 and all(abs(sum(c * c for c in v) - 1.0) < 1e-12 for v in pn.randvec)
+    for perm in (pn.perm_x, pn.perm_y, pn.perm_z):
+        assert sorted(perm) == list(range(256))
+        # `gen_range(0..i)` excludes i (perlin.rs:84): the shuffle is Sattolo's — one cycle, no fixed point
+        assert all(perm[i] != i for i in range(256))
+    assert pn.perm_x != pn.perm_y != pn.perm_z
+    # lattice points: every weight vector is a lattice offset and the corner's own weight is 1 -> noise = c . 0 = 0
+    assert pn.noise((3.0, -2.0, 7.0)) == 0.0
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-30, 30, size=(500, 3))
+    vals = np.array([pn.noise(tuple(p)) for p in pts])
+    assert np.abs(vals).max() <= 1.0 and vals.std() > 0.1  # "in the range [-1, 1]" (perlin.rs:38)
+    desc = ow.lower_world(world)
+    tex = desc.materials[0].texture
+    uvp = np.concatenate([np.zeros((500, 2)), pts], axis=1)
+    got = oracle.ow_tex_value(desc, tex, uvp)
+    exp = np.array([noise.value(0.0, 0.0, tuple(p)) for p in pts])
+    assert np.allclose(got, exp, rtol=0, atol=1e-12)
+    assert (got >= 0).all() and (got <= 1).all() and got.std() > 0.05
+
+
+def test_constant_medium_lowering_and_oracle_statistics(oracle):
+    """constant_medium.rs: a unit-density slab of thickness L transmits exp(-L) of the straight-through rays"""
+    black = ow.Isotropic(ow.SolidColor((0.0, 0.0, 0.0)))  # absorbs: a scattered path carries nothing
+    wall = ow.Lambertian(ow.SolidColor((0.5, 0.5, 0.5)))
+    box = ow.HittableList(scenes._ow_box((-50.0, -50.0, -1.0), (50.0, 50.0, 0.0), wall))
+    world = [ow.ConstantMedium.new(box, 1.5, black)]
+    desc = ow.lower_world(world)
+    kinds = [n[0] for n in desc.nodes]
+    assert kinds.count(A.RL_OW_CONSTANT_MEDIUM) == 1 and kinds.count(A.RL_OW_QUAD) == 6
+    assert desc.materials[desc.nodes[kinds.index(A.RL_OW_CONSTANT_MEDIUM)][1]].kind == A.RL_MAT_OW_ISOTROPIC
+    params = ow.CameraParams(aspect_ratio=1.0, image_width=8, samples_per_pixel=4000, max_depth=10, vfov=1.0,
+                             lookfrom=(0.0, 0.0, 5.0), lookat=(0.0, 0.0, 0.0), vup=(0.0, 1.0, 0.0),
+                             background=(1.0, 1.0, 1.0), seed=5)
+    sums, _ = oracle.ow_render(desc, params.abi())
+    mean = sums.mean() / 4000
+    assert abs(mean - math.exp(-1.5)) < 0.01, mean
+    # zero density: -1/0 = -inf in f64, the medium never scatters (no panic in the reference either)
+    sums, _ = oracle.ow_render(ow.lower_world([ow.ConstantMedium.new(box, 0.0, black)]), params.abi())
+    assert np.allclose(sums / 4000, 1.0)
