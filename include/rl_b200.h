@@ -270,6 +270,16 @@ int rl_render_rtc(rl_ctx* ctx, const rl_rtc_camera* cam, uint32_t anti_aliasing_
  * image height = max(1, trunc(image_width / aspect_ratio)) (camera.rs:75). */
 int rl_render_ow(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sample,
                  float* out_rgb_sum, rl_stats* stats);
+/* The same renders with the reference's 8-bit output encoders run on the device, so the D2H copy is
+ * 3 bytes per pixel instead of 12; out_rgb8 = W*H*3 bytes, row-major.
+ *   RTC: Canvas::ppm's `translate` (RTC/src/draw/canvas.rs:53-56): round(c * 255) half away from zero, clamped to [0,255].
+ *   OW : Canvas::pixel_data + Color::write_ppm (OW/src/camera.rs:293-295, color.rs:22-57, 130-136):
+ *        c = sum * (1 / samples); linear_to_srgb; floor(c * 255.999) clamped to [0,255].
+ * Both are evaluated in f64 from the f32 framebuffer, i.e. exactly what the reference's encoder makes of the values
+ * rl_render_rtc / rl_render_ow return. */
+int rl_render_rtc_u8(rl_ctx* ctx, const rl_rtc_camera* cam, uint32_t anti_aliasing_samples, uint8_t* out_rgb8,
+                     rl_stats* stats);
+int rl_render_ow_u8(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sample, uint8_t* out_rgb8, rl_stats* stats);
 int rl_ow_image_height(const rl_ow_camera* cam);
 /* number of sample chunks the OW renderer splits samples_per_pixel into (deterministic reduction) */
 int rl_ow_num_chunks(const rl_ow_camera* cam);

@@ -182,6 +182,8 @@ SYMBOLS = {
                                 C.POINTER(rl_stats)]),
     "rl_render_ow": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(C.c_float),
                                C.POINTER(rl_stats)]),
+    "rl_render_rtc_u8": (C.c_int, [_P, C.POINTER(rl_rtc_camera), C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(rl_stats)]),
+    "rl_render_ow_u8": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(rl_stats)]),
     "rl_ow_image_height": (C.c_int, [C.POINTER(rl_ow_camera)]),
     "rl_ow_num_chunks": (C.c_int, [C.POINTER(rl_ow_camera)]),
     "rl_render_rtc_device": (C.c_int, [_P, C.POINTER(rl_rtc_camera), C.c_uint32,

@@ -122,6 +122,22 @@ class Context:
                                            C.byref(stats)))
         return out, stats
 
+    def render_rtc_u8(self, cam: A.rl_rtc_camera, aa_samples: int = 1):
+        """render + Canvas::ppm's 8-bit `translate` on the device: [H][W][3] uint8"""
+        out = np.empty((cam.vsize, cam.hsize, 3), np.uint8)
+        stats = A.rl_stats()
+        self._check(self.lib.rl_render_rtc_u8(self.h, C.byref(cam), C.c_uint32(aa_samples),
+                                              out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(stats)))
+        return out, stats
+
+    def render_ow_u8(self, cam: A.rl_ow_camera, first_sample: int = 0):
+        """render + pixel_data / linear_to_srgb / to_u8 on the device: [H][W][3] uint8"""
+        out = np.empty((self.ow_image_height(cam), cam.image_width, 3), np.uint8)
+        stats = A.rl_stats()
+        self._check(self.lib.rl_render_ow_u8(self.h, C.byref(cam), C.c_uint32(first_sample),
+                                             out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(stats)))
+        return out, stats
+
     def ow_image_height(self, cam: A.rl_ow_camera) -> int:
         return int(self.lib.rl_ow_image_height(C.byref(cam)))
 

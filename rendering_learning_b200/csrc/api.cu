@@ -62,7 +62,7 @@ struct rl_ctx {
     float upload_ms = 0.0f;
     int upload_launches = 0;
     // work buffers
-    DevBuf counters, queue, jobs, prefix, frame, partial, rays, hits;
+    DevBuf counters, queue, jobs, prefix, frame, frame8, partial, rays, hits;
     // cross-GPU queue (CUDA IPC): the owner allocates it, peers map it
     DevBuf shared_queue_own, shared_partial_own;
     float* shared_partial = nullptr;
@@ -158,7 +158,7 @@ void rl_destroy(rl_ctx* c) {
                      &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
-                     &c->jobs, &c->prefix, &c->frame, &c->partial, &c->rays, &c->hits};
+                     &c->jobs, &c->prefix, &c->frame, &c->frame8, &c->partial, &c->rays, &c->hits};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->image_texels) b.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -517,6 +517,25 @@ int rl_render_rtc(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, float* out_r
     return RL_OK;
 }
 
+int rl_render_rtc_u8(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, uint8_t* out_rgb8, rl_stats* stats) {
+    if (!c || !cam || !out_rgb8) return RL_E_INVALID;
+    if (cam->hsize < 1 || cam->vsize < 1) return fail(c, RL_E_INVALID, "empty image");
+    size_t n = (size_t)cam->hsize * cam->vsize * 3;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->frame.reserve(n * sizeof(float)));
+    CK(c, c->frame8.reserve(n));
+    rl_job job{0, 0, cam->hsize, cam->vsize, 0, 1};
+    rl_stats st{};
+    int rc = rl_render_rtc_device(c, cam, aa, &job, 1, c->frame.p, nullptr, &st);
+    if (rc != RL_OK) return rc;
+    CK(c, launch_encode_rtc_u8(c->frame.as<float>(), c->frame8.as<uint8_t>(), n, c->stream));
+    CK(c, cudaMemcpyAsync(out_rgb8, c->frame8.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    st.kernel_launches += 1;
+    if (stats) *stats = st;
+    return RL_OK;
+}
+
 int rl_ow_image_height(const rl_ow_camera* cam) { return cam ? ow_image_height(cam) : 0; }
 int rl_ow_num_chunks(const rl_ow_camera* cam) { return cam ? ow_num_chunks(cam->samples_per_pixel) : 0; }
 
@@ -657,8 +676,8 @@ int rl_ow_reduce_device(rl_ctx* c, const rl_ow_camera* cam, const void* d_partia
     return RL_OK;
 }
 
-int rl_render_ow(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, float* out_rgb_sum, rl_stats* stats) {
-    if (!c || !cam || !out_rgb_sum) return RL_E_INVALID;
+// renders into c->frame (sums); shared by rl_render_ow and rl_render_ow_u8
+static int render_ow_to_frame(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, rl_stats* st, size_t* frame_bytes) {
     if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0))
         return fail(c, RL_E_INVALID, "bad camera parameters");
     int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
@@ -667,18 +686,45 @@ int rl_render_ow(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, floa
     CK(c, c->partial.reserve(frame / 3 * 4 * nc));  // [n_chunks][H][W] float4
     CK(c, c->frame.reserve(frame));
     rl_job job{0, 0, cam->image_width, H, 0, nc};
-    rl_stats st{};
-    int rc = rl_render_ow_device(c, cam, first_sample, &job, 1, c->partial.p, nullptr, &st);
+    int rc = rl_render_ow_device(c, cam, first_sample, &job, 1, c->partial.p, nullptr, st);
     if (rc != RL_OK) return rc;
     CK(c, cudaEventRecord(c->ev0, c->stream));
     rc = rl_ow_reduce_device(c, cam, c->partial.p, c->frame.p, nullptr);
     if (rc != RL_OK) return rc;
     CK(c, cudaEventRecord(c->ev1, c->stream));
-    CK(c, cudaMemcpyAsync(out_rgb_sum, c->frame.p, frame, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     float ms = 0.0f;
     CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    st.kernel_ms += ms;
+    st->kernel_ms += ms;
+    st->kernel_launches += 1;
+    *frame_bytes = frame;
+    return RL_OK;
+}
+
+int rl_render_ow(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, float* out_rgb_sum, rl_stats* stats) {
+    if (!c || !cam || !out_rgb_sum) return RL_E_INVALID;
+    rl_stats st{};
+    size_t frame = 0;
+    int rc = render_ow_to_frame(c, cam, first_sample, &st, &frame);
+    if (rc != RL_OK) return rc;
+    CK(c, cudaMemcpyAsync(out_rgb_sum, c->frame.p, frame, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (stats) *stats = st;
+    return RL_OK;
+}
+
+int rl_render_ow_u8(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, uint8_t* out_rgb8, rl_stats* stats) {
+    if (!c || !cam || !out_rgb8) return RL_E_INVALID;
+    rl_stats st{};
+    size_t frame = 0;
+    int rc = render_ow_to_frame(c, cam, first_sample, &st, &frame);
+    if (rc != RL_OK) return rc;
+    size_t n = frame / sizeof(float);
+    CK(c, c->frame8.reserve(n));
+    // Canvas.samples of a fresh render = samples_per_pixel; a resumed render is merged on the host (sums), not here
+    CK(c, launch_encode_ow_u8(c->frame.as<float>(), c->frame8.as<uint8_t>(), n, cam->samples_per_pixel, c->stream));
+    CK(c, cudaMemcpyAsync(out_rgb8, c->frame8.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     st.kernel_launches += 1;
     if (stats) *stats = st;
     return RL_OK;

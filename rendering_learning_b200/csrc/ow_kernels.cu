@@ -829,6 +829,24 @@ __global__ void k_ow_reduce(const float4* __restrict__ partial, float* __restric
     out[3 * i + 2] = b;
 }
 
+// ---- 8-bit output encoders ------------------------------------------------------------------------------------
+// f64 on purpose: these must agree bit for bit with the reference's encoders applied to the f32 framebuffer.
+__global__ void k_encode_rtc_u8(const float* __restrict__ rgb, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = (double)rgb[i] * 255.0;  // canvas.rs:53-56: `(color * 255).round() as i32`, clamp(0, 255)
+    double r = round(v);                // half away from zero, like f64::round
+    out[i] = (uint8_t)(r != r ? 0.0 : fmin(fmax(r, 0.0), 255.0));  // `NaN as i32` is 0
+}
+__global__ void k_encode_ow_u8(const float* __restrict__ sum, uint8_t* __restrict__ out, size_t n, double inv_samples) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = (double)sum[i] * inv_samples;  // `c / samples` is `c * (1.0 / samples)` (vec3.rs:178-184)
+    double s = v <= 0.0031308 ? 12.92 * v : 1.055 * pow(v, 1.0 / 2.4) - 0.055;  // color.rs:130-136
+    double f = floor(s * 255.999);                                              // color.rs:47-57, `as i16` saturates
+    out[i] = (uint8_t)(f != f ? 0.0 : fmin(fmax(f, 0.0), 255.0));
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_ow_trace(DevScene sc, const rl_ray* __restrict__ rays, unsigned long long n,
                                                   rl_hit* __restrict__ hits, Counters* counters) {
@@ -996,6 +1014,18 @@ cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, fl
     size_t n = (size_t)cam->image_width * ow_image_height(cam);
     int nc = ow_num_chunks(cam->samples_per_pixel);
     k_ow_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(d_partial), d_out, n, nc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_rtc_u8(const float* d_rgb, uint8_t* d_out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_encode_rtc_u8<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_rgb, d_out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_ow_u8(const float* d_rgb_sum, uint8_t* d_out, size_t n, int samples, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_encode_ow_u8<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_rgb_sum, d_out, n, 1.0 / (double)samples);
     return cudaGetLastError();
 }
 

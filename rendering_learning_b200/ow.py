@@ -513,6 +513,27 @@ class Canvas:
         assert self.data.size == other.data.size
         return Canvas(self.samples + other.samples, self.width, self.height, self.data + other.data)
 
+    # ---- bincode 1.3.3 image of `#[derive(Serialize, Deserialize)] struct Canvas` (camera.rs:263-270), the
+    # checkpoint format of examples/common/mod.rs:24-56: usize fields as u64 LE, `Vec<Color>` as a u64 length
+    # followed by the elements, a `Color` = `Vec3([f64; 3])` as three f64 LE (fixed-size arrays carry no length)
+    def to_bincode(self) -> bytes:
+        import struct
+        head = struct.pack("<QQQQ", self.samples, self.width, self.height, self.width * self.height)
+        return head + np.ascontiguousarray(self.data, "<f8").tobytes()
+
+    @classmethod
+    def from_bincode(cls, blob: bytes) -> "Canvas":
+        import struct
+        if len(blob) < 32:
+            raise ValueError("io error: unexpected end of file")  # bincode's ErrorKind::Io
+        samples, width, height, n = struct.unpack_from("<QQQQ", blob, 0)
+        if len(blob) < 32 + 24 * n:
+            raise ValueError("io error: unexpected end of file")
+        data = np.frombuffer(blob, "<f8", count=3 * n, offset=32)
+        if n != width * height:
+            raise ValueError("checkpoint pixel count does not match width x height")
+        return cls(samples, width, height, data.copy())
+
     def pixel_data(self) -> np.ndarray:
         # `c / samples` is `c * (1.0 / samples)` (vec3.rs:178-184)
         return self.data * (1.0 / float(self.samples))

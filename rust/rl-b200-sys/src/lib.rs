@@ -274,6 +274,10 @@ extern "C" {
                          stats: *mut rl_stats) -> c_int;
     pub fn rl_render_ow(ctx: *mut rl_ctx, cam: *const rl_ow_camera, first_sample: u32, out_rgb_sum: *mut f32,
                         stats: *mut rl_stats) -> c_int;
+    pub fn rl_render_rtc_u8(ctx: *mut rl_ctx, cam: *const rl_rtc_camera, anti_aliasing_samples: u32, out_rgb8: *mut u8,
+                            stats: *mut rl_stats) -> c_int;
+    pub fn rl_render_ow_u8(ctx: *mut rl_ctx, cam: *const rl_ow_camera, first_sample: u32, out_rgb8: *mut u8,
+                           stats: *mut rl_stats) -> c_int;
     pub fn rl_ow_image_height(cam: *const rl_ow_camera) -> c_int;
     pub fn rl_ow_num_chunks(cam: *const rl_ow_camera) -> c_int;
 

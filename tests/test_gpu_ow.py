@@ -203,3 +203,18 @@ def test_full_size_cover_properties(ctx):
     m = a.mean() / 8
     assert 0.25 < m < 0.6  # sky-lit scene
     assert st.samples == 1200 * 675 * 8
+
+
+def test_device_side_u8_encoder_matches_the_reference_encoder(ctx):
+    """pixel_data / linear_to_srgb / to_u8 on the device == the host encoder on the returned sums"""
+    world, params = scenes.ow_test_scene()
+    params.samples_per_pixel = 12
+    ctx.scene_upload(ow.lower_world(world))
+    sums, _ = ctx.render_ow(params.abi())
+    u8, st = ctx.render_ow_u8(params.abi())
+    exp = ow.Canvas(12, params.image_width, sums.shape[0], sums).to_u8()
+    assert u8.dtype == np.uint8 and np.array_equal(u8.astype(np.int64), exp)
+    assert u8.max() > 128
+    # a checkpoint written from the device render resumes on the host types unchanged
+    cv = ow.Canvas(12, params.image_width, sums.shape[0], sums)
+    assert ow.Canvas.from_bincode(cv.to_bincode()) == cv

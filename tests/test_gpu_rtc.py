@@ -271,3 +271,13 @@ def test_full_size_properties(ctx, name, builder):
     for j in jobs[::2] + jobs[1::2]:
         ctx.render_rtc_device(cam, 1, [j], buf.data_ptr())
     assert np.array_equal(buf.cpu().numpy(), a)
+
+
+def test_device_side_u8_encoder_matches_canvas_ppm(ctx):
+    """SURVEY §8f.3: Canvas::ppm's `translate` on the device == the host encoder on the returned floats,
+    including the clamped highlights (> 1.0) of the mirror scene"""
+    sc = scenes.rtc_mirror_scene(300, 200)
+    ctx.scene_upload(sc.world.lower())
+    img, _ = ctx.render_rtc(sc.camera.abi(), 1)
+    u8dev, _ = ctx.render_rtc_u8(sc.camera.abi(), 1)
+    assert img.max() > 1.0 and np.array_equal(u8dev.astype(np.int64), u8(img.astype(np.float64)))

@@ -169,3 +169,20 @@ def test_constant_medium_lowering_and_oracle_statistics(oracle):
     # zero density: -1/0 = -inf in f64, the medium never scatters (no panic in the reference either)
     sums, _ = oracle.ow_render(ow.lower_world([ow.ConstantMedium.new(box, 0.0, black)]), params.abi())
     assert np.allclose(sums / 4000, 1.0)
+
+
+def test_ow_checkpoint_bincode_layout():
+    """the reference's checkpoint files (examples/common/mod.rs:24-56) are bincode 1.3.3 of `Canvas` (camera.rs:263-270)"""
+    import struct
+    data = np.arange(2 * 3 * 3, dtype=np.float64).reshape(2, 3, 3) * 0.25
+    cv = ow.Canvas(7, 3, 2, data)
+    blob = cv.to_bincode()
+    assert len(blob) == 4 * 8 + 6 * 24
+    assert struct.unpack_from("<QQQQ", blob) == (7, 3, 2, 6)  # samples, width, height, Vec<Color> length
+    assert struct.unpack_from("<ddd", blob, 32 + 24 * 4) == (3.0, 3.25, 3.5)  # pixel (x=1, y=1), row-major
+    back = ow.Canvas.from_bincode(blob)
+    assert back == cv and back.samples == 7
+    merged = back.merge(cv)  # resume semantics: sums add, samples add (camera.rs:273-291)
+    assert merged.samples == 14 and np.array_equal(merged.data, 2 * data)
+    with pytest.raises(ValueError):
+        ow.Canvas.from_bincode(blob[:-1])
