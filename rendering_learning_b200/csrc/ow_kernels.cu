@@ -294,7 +294,9 @@ __device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, flo
         pre.kx = sh.k & 3; pre.ky = (sh.k >> 2) & 3; pre.kz = (sh.k >> 4) & 3;
         pre.Sx = sh.Sx; pre.Sy = sh.Sy; pre.Sz = sh.Sz;
     }
-    ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, dot(d, d), time, self_ref, tmin, h, lc, ray_rnd);
+    // the v5 kernel normalises every ray direction when its traversal starts, so a = d.d is the CONSTANT 1 here and
+    // the divisions by it in the sphere test fold away (they were ~16 instructions per test)
+    ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, 1.0f, time, self_ref, tmin, h, lc, ray_rnd);
 }
 
 // world.hit(r, [tmin, inf)) through the LBVH (callback form; used by rl_trace_batch and the v1 kernel).
@@ -471,17 +473,18 @@ __device__ __forceinline__ void chunk_range(int spp, int n_chunks, int chunk, in
 __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, unsigned sample, Path& p) {
     uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
     unsigned pixel = (unsigned)(j * cam.width + i);
+    // ONE Philox call per camera ray: the sub-pixel jitter takes the two 16-bit halves of one word (1/65536 of a pixel
+    // is far below what a sample count can resolve), time and the two defocus-disc coordinates a word each
     uint4 r = philox(make_uint4(pixel, sample, 0u, 0u), key);
     float3 center = cam.pixel00 + cam.du * (float)i + cam.dv * (float)j;
-    float px = -0.5f + u01(r.x), py = -0.5f + u01(r.y);
+    float px = -0.5f + (float)(r.x >> 16) * (1.0f / 65536.0f), py = -0.5f + (float)(r.x & 0xffffu) * (1.0f / 65536.0f);
     float3 sample_p = center + cam.du * px + cam.dv * py;
     float3 origin = cam.lookfrom;
     if (cam.defocus) {
         // uniform point in the unit disc (polar map; UnitDisc's rejection loop is statistically identical)
         float rr = sqrtf(u01(r.w));
-        uint4 r2 = philox(make_uint4(pixel, sample, 0u, 1u), key);
         float s, c;
-        sincospif(2.0f * u01(r2.x), &s, &c);
+        sincospif(2.0f * u01(r.y), &s, &c);
         origin = cam.lookfrom + cam.disk_u * (rr * c) + cam.disk_v * (rr * s);
     }
     p.o = origin;
@@ -746,9 +749,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             alive = true;
         }
         if (svc && alive) {  // start the traversal of the lane's new ray
+            // unit direction: t is internal to this kernel (hit point = o + d t either way), and with |d| = 1 the
+            // sphere quadratic, the medium's ray length and the tmin scale lose their divisions by d.d
+            p.d = p.d * rsqrtf(dot(p.d, p.d));
             inv_d = f3(1.0f / p.d.x, 1.0f / p.d.y, 1.0f / p.d.z);
             oi = p.o * inv_d;
-            tmin = ow_tmin(p);
+            tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // ow_tmin with |d| = 1
             if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
             if (PRIMS & PRIMS_MEDIA)
                 ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
