@@ -969,7 +969,7 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     //  ncu summaries stay under profiles/.)
     static const int variant = env_int("RL_OW_KERNEL_V", 5);
     static const int minb_env = env_int("RL_OW_MINB", 0);
-    static const int svc_min = env_int("RL_OW_SVC", 16), leaf_min = env_int("RL_OW_LEAF", 12);
+    static const int svc_env = env_int("RL_OW_SVC", 0), leaf_min = env_int("RL_OW_LEAF", 12);
     static const int generic = env_int("RL_OW_GENERIC", 0);  // 1: never pick the spheres-only instantiation
     typedef void (*K3)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
     typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
@@ -982,6 +982,9 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     // 64 registers (4 CTAs/SM) with 18 / 86 B of spills and win there (C5 @64 spp: 66.7 vs 69.4 ms); the build that
     // carries every primitive kind is better at 80 registers (3 CTAs/SM)
     const int minb = minb_env ? minb_env : ((spheres_only || no_spheres) ? 4 : 3);
+    // service threshold (profiles/r01_sweep_ow_v5b.log): sphere scenes shade cheaply and prefer fuller service rounds
+    // (C4: 12.50 ms at 24 vs 13.25 at 16); with triangles in the leaf rounds 16 is best (C5: 67.0 vs 74.0 at 24)
+    const int svc_min = svc_env ? svc_env : (spheres_only ? 24 : 16);
     constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
     if (variant == 3 && !extras) {  // v3 predates media / Noise
         k3 = instrumented ? (K3)k_ow_render<true, 1, 4> : (K3)k_ow_render<false, 1, 4>;
