@@ -15,7 +15,9 @@ gathered to rank 0 with NCCL.  Rank 0 prints ONE JSON line.
              render, D2H of the framebuffer into pinned host memory, every step.
   roofline   algorithmic FP32 flops (SURVEY.md §8d constants x device counters) / kernel time vs the FP32
              peak measured live on this GPU; L2 and HBM fractions beside it.  bound = "fp32": no stage of this
-             path is a dense contraction and the working set is L1/L2 resident.
+             path is a dense contraction and the working set is L1/L2 resident.  `traffic` =
+             dram__bytes_read + dram__bytes_write of the same kernel at the same config from the committed
+             `ncu --set full` capture (profiles/ncu_<workload>.json, written by tools/ncu_traffic.py).
   cpu_baseline  the oracle (a C++ f64 restatement of the reference; the Rust reference cannot be built in
              this image) on all host cores, on a bounded sample of the same workload.
 """
@@ -437,7 +439,8 @@ def main():
         prof = json.load(open(pj))
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
                 "frac": ach_tf / peaks["fp32_tflops"], "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_ow_render" if wl["kind"] == "ow" else "k_rtc_render", "kernel_ms": kms,
+                "kernel": "k_ow_render5" if wl["kind"] == "ow" else "k_rtc_render", "kernel_ms": kms,
+                "traffic_source": prof.get("source"),
                 "flops_per_launch": fl, "peak_source": "measured live (rl_measure_peaks: FMA chains, all SMs)",
                 "l2": {"achieved": by / (kms * 1e-3) / 1e9, "peak": peaks["l2_gbs"], "unit": "GB/s",
                        "frac": by / (kms * 1e-3) / 1e9 / peaks["l2_gbs"], "bytes_per_launch": by},
