@@ -421,6 +421,10 @@ def main():
             dist.destroy_process_group()
         return
 
+    # the image of the last timed step: identical for every GPU count / tile schedule (compare across --gpus runs)
+    import hashlib
+    torch.cuda.synchronize()
+    frame_md5 = hashlib.md5(frame.detach().cpu().numpy().tobytes()).hexdigest()
     rays = st_i["rays"]
     value = rays / (ms_per_step * 1e-3) / 1e6
     fl, by = algorithmic(wl["kind"], st_i, samples)
@@ -460,7 +464,7 @@ def main():
                                         else f"{len(jobs)} tile x sample-chunk jobs from a c10d-store queue, NCCL sum-gather to rank 0") +
                                        f", {world_size} ranks") if world_size > 1 else "1 rank, persistent warps"},
             "samples_per_s": samples / (ms_per_step * 1e-3), "rays_per_step": rays, "samples_per_step": samples,
-            "wall_s_timed_region": t_wall, "step_ms": step_ms,
+            "wall_s_timed_region": t_wall, "step_ms": step_ms, "frame_md5": frame_md5,
             "clocks": clocks, "gpu_launches": total_launches,
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_n,

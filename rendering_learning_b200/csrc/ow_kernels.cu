@@ -890,7 +890,8 @@ static int env_int(const char* name, int dflt) {
 int ow_num_chunks(int spp) {
     if (spp <= 0) return 1;
     static const int min_chunk = env_int("RL_OW_CHUNK", 8);  // experiments only: every rank must agree
-    int per_chunk = (spp + 63) / 64;
+    static const int max_chunks = env_int("RL_OW_MAXCHUNKS", 64);
+    int per_chunk = (spp + max_chunks - 1) / max_chunks;
     if (per_chunk < min_chunk) per_chunk = min_chunk;
     return (spp + per_chunk - 1) / per_chunk;
 }
