@@ -374,6 +374,54 @@ def ow_cornell_smoke():
     return world, params
 
 
+def ow_final_scene(image_width=400, samples_per_pixel=250, max_depth=4):
+    """OW/examples/final_scene.rs:35-258 — the "next week" final scene: 400 ground boxes in a Bvh, a light, a moving
+    sphere, glass, fuzzy metal, a glass sphere filled with a blue ConstantMedium, a global fog (radius-5000 boundary),
+    an image-textured globe, a Perlin sphere and a rotated + translated Bvh of 1000 small spheres.  The reference embeds
+    examples/files/earthmap.jpg; this builder uses a procedural 256 x 128 map instead (no binary asset travels), which
+    is irrelevant to parity: oracle and device consume the same description."""
+    from . import ow
+    rng = _Xoshiro256PlusPlus(0)
+    ground = ow.Lambertian(ow.SolidColor((0.48, 0.83, 0.53)))
+    light = ow.DiffuseLight(ow.SolidColor((7.0, 7.0, 7.0)))
+    sphere_material = ow.Lambertian(ow.SolidColor((0.7, 0.3, 0.1)))
+    glass = ow.Dielectric(1.5)
+    metal = ow.Metal((0.8, 0.8, 0.9), 1.0)
+    subsurface = ow.Isotropic(ow.SolidColor((0.2, 0.4, 0.9)))
+    fog = ow.Isotropic(ow.SolidColor((1.0, 1.0, 1.0)))
+    v, u = np.meshgrid(np.linspace(0, 1, 128), np.linspace(0, 1, 256), indexing="ij")
+    srgb_map = np.stack([0.5 + 0.5 * np.sin(12 * np.pi * u), 0.5 + 0.5 * np.cos(6 * np.pi * v), 0.3 + 0.4 * u * v], axis=2)
+    earth = ow.Lambertian(ow.Image(ow.srgb.srgb_to_linear(srgb_map).astype(np.float32)))
+    perlin = ow.Lambertian(ow.Noise(ow.Perlin.new(rng), 0.2))
+    white = ow.Lambertian(ow.SolidColor((0.73, 0.73, 0.73)))
+    world = []
+    boxes = []
+    for i in range(20):
+        for j in range(20):
+            w = 100.0
+            x0, z0, y0 = -1000.0 + i * w, -1000.0 + j * w, 0.0
+            y1 = rng.gen_range(1.0, 101.0)
+            boxes.append(ow.HittableList(_ow_box((x0, y0, z0), (x0 + w, y1, z0 + w), ground)))
+    world.append(ow.Bvh.new(boxes))
+    world.append(ow.Quad.new((123.0, 554.0, 147.0), (300.0, 0.0, 0.0), (0.0, 0.0, 265.0), light))
+    world.append(ow.Sphere(ow.Center.Moving((400.0, 400.0, 200.0), (430.0, 400.0, 200.0)), 50.0, sphere_material))
+    world.append(ow.Sphere(ow.Center.Stationary((260.0, 150.0, 45.0)), 50.0, glass))
+    world.append(ow.Sphere(ow.Center.Stationary((0.0, 150.0, 145.0)), 50.0, metal))
+    boundary = lambda: ow.Sphere(ow.Center.Stationary((360.0, 150.0, 145.0)), 70.0, glass)
+    world.append(boundary())
+    world.append(ow.ConstantMedium.new(boundary(), 0.2, subsurface))
+    world.append(ow.ConstantMedium.new(ow.Sphere(ow.Center.Stationary((0.0, 0.0, 0.0)), 5000.0, glass), 0.0001, fog))
+    world.append(ow.Sphere(ow.Center.Stationary((400.0, 200.0, 400.0)), 100.0, earth))
+    world.append(ow.Sphere(ow.Center.Stationary((220.0, 280.0, 300.0)), 80.0, perlin))
+    small = [ow.Sphere(ow.Center.Stationary((rng.gen_range(0.0, 165.0), rng.gen_range(0.0, 165.0), rng.gen_range(0.0, 165.0))),
+                       10.0, white) for _ in range(1000)]
+    world.append(ow.Bvh.new(small).rotate_y(15.0).translate((-100.0, 270.0, 395.0)))
+    params = ow.CameraParams(aspect_ratio=1.0, image_width=image_width, samples_per_pixel=samples_per_pixel,
+                             max_depth=max_depth, vfov=40.0, lookfrom=(478.0, 278.0, -600.0), lookat=(278.0, 278.0, 0.0),
+                             vup=(0.0, 1.0, 0.0), defocus_angle=0.0, background=(0.0, 0.0, 0.0))
+    return world, params
+
+
 def ow_spot_texture() -> np.ndarray:
     """cow.rs:19-30: decode -> into_rgb32f (u8/255 as f32) -> srgb_to_linear in f64 -> f32."""
     from . import ow

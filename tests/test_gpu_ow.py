@@ -36,6 +36,10 @@ def _small(builder, width):
 EXTRA_CASES = {
     "perlin_spheres": lambda: _small(scenes.ow_perlin_spheres, 200),
     "cornell_smoke": lambda: _small(scenes.ow_cornell_smoke, 120),
+    # examples/final_scene.rs: everything at once — Bvh of boxes, moving sphere, glass / metal, a medium inside a glass
+    # sphere, a global fog whose boundary is a radius-5000 sphere (big list, f64 quadratic), image-textured globe
+    # (sphere uv), Perlin sphere, a rotated + translated Bvh of 1000 spheres
+    "final_scene": lambda: scenes.ow_final_scene(image_width=120, samples_per_pixel=32, max_depth=20),
 }
 
 
@@ -107,7 +111,7 @@ def test_psnr_noise_and_media(ctx, oracle, name):
     p_gpu, p_cpu = psnr(gpu, ref_hi), psnr(cpu, ref_hi)
     assert p_gpu >= p_cpu - 0.5, (p_gpu, p_cpu)
     m_gpu, m_hi = sums.mean() / spp, o_hi.mean() / (8 * spp)
-    assert abs(m_gpu - m_hi) <= 0.02 * m_hi, (m_gpu, m_hi)
+    assert abs(m_gpu - m_hi) <= (0.05 if name == "final_scene" else 0.02) * m_hi, (m_gpu, m_hi)  # small light: noisier mean
 
 
 def test_medium_transmission_is_beer_lambert(ctx):
