@@ -252,6 +252,10 @@ int rl_measure_peaks(rl_ctx* ctx, double* fp32_tflops, double* l2_gbs, double* h
  * flattens the tree, uploads SoA buffers and builds the LBVH on the device. */
 int rl_scene_upload(rl_ctx* ctx, const rl_scene_desc* scene);
 int rl_scene_info_get(rl_ctx* ctx, rl_scene_info* out);
+/* The HOST half of rl_scene_upload on its own (no device needed): validates and flattens the description exactly like
+ * the upload does and reports what it would produce; `err` (optional, err_cap bytes) receives the message on failure.
+ * Lets a caller reject a scene the device path cannot lower (RL_E_UNSUPPORTED) before committing to it. */
+int rl_scene_check(const rl_scene_desc* scene, rl_scene_info* out, char* err, int32_t err_cap);
 int rl_lbvh_download(rl_ctx* ctx, rl_lbvh_host* out);
 
 /* ---- ray batches -------------------------------------------------------------------------------- */

@@ -176,6 +176,7 @@ SYMBOLS = {
     "rl_measure_peaks": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rl_scene_upload": (C.c_int, [_P, C.POINTER(rl_scene_desc)]),
     "rl_scene_info_get": (C.c_int, [_P, C.POINTER(rl_scene_info)]),
+    "rl_scene_check": (C.c_int, [C.POINTER(rl_scene_desc), C.POINTER(rl_scene_info), C.c_char_p, C.c_int32]),
     "rl_lbvh_download": (C.c_int, [_P, C.POINTER(rl_lbvh_host)]),
     "rl_trace_batch": (C.c_int, [_P, C.POINTER(rl_ray), C.c_uint64, C.POINTER(rl_hit)]),
     "rl_render_rtc": (C.c_int, [_P, C.POINTER(rl_rtc_camera), C.c_uint32, C.POINTER(C.c_float),

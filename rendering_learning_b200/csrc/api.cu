@@ -92,9 +92,43 @@ static cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
+// what a flattened scene will occupy / contain (shared by rl_scene_upload and the host-only rl_scene_check)
+static rl_scene_info scene_info_of(const FlatScene& fs) {
+    rl_scene_info si{};
+    const int n = (int)fs.bvh_ref.size();
+    const int nn = n >= 2 ? n - 1 : (n == 1 ? 1 : 0);
+    size_t image_bytes = 0;
+    for (const auto& im : fs.images) image_bytes += im.texels.size() * sizeof(float4);
+    si.flavor = fs.flavor;
+    si.n_prims = fs.flavor == RL_FLAVOR_OW ? (int)fs.big_refs.size() : (int)fs.prims.size();
+    si.n_bvh_prims = n;
+    si.n_bvh_nodes = n >= 2 ? n - 1 : 0;
+    si.n_materials = (int)fs.materials.size();
+    si.n_textures = (int)fs.textures.size();
+    si.n_lights = (int)fs.lights.size();
+    si.has_transparency = fs.has_transparency;
+    si.device_bytes = (int64_t)(fs.prims.size() * sizeof(RtcPrim) + fs.tri_verts.size() * (sizeof(TriVerts) + sizeof(TriShade)) +
+                                fs.spheres.size() * sizeof(OwSphere) + fs.quads.size() * sizeof(OwQuad) +
+                                (size_t)nn * sizeof(BvhNode) + image_bytes + fs.materials.size() * sizeof(DevMaterial));
+    return si;
+}
+
 extern "C" {
 
 int rl_abi_version(void) { return RL_B200_ABI_VERSION; }
+
+int rl_scene_check(const rl_scene_desc* scene, rl_scene_info* out, char* err, int32_t err_cap) {
+    FlatScene fs;
+    std::string msg;
+    int rc = flatten_scene(scene, &fs, &msg);
+    if (err && err_cap > 0) {
+        size_t k = msg.size() < (size_t)(err_cap - 1) ? msg.size() : (size_t)(err_cap - 1);
+        memcpy(err, msg.data(), k);
+        err[k] = 0;
+    }
+    if (rc == RL_OK && out) *out = scene_info_of(fs);
+    return rc;
+}
 
 const char* rl_last_error(const rl_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
@@ -329,19 +363,7 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     d.perlin_vec = c->perlin_vec.as<float4>();
     d.perlin_perm = c->perlin_perm.as<int>();
 
-    rl_scene_info& si = c->info;
-    si = rl_scene_info{};
-    si.flavor = fs.flavor;
-    si.n_prims = d.flavor == RL_FLAVOR_OW ? d.n_big : d.n_prims;
-    si.n_bvh_prims = n;
-    si.n_bvh_nodes = n >= 2 ? n - 1 : 0;
-    si.n_materials = d.n_materials;
-    si.n_textures = d.n_textures;
-    si.n_lights = d.n_lights;
-    si.has_transparency = d.has_transparency;
-    si.device_bytes = (int64_t)(fs.prims.size() * sizeof(RtcPrim) + fs.tri_verts.size() * (sizeof(TriVerts) + sizeof(TriShade)) +
-                                fs.spheres.size() * sizeof(OwSphere) + fs.quads.size() * sizeof(OwQuad) +
-                                (size_t)nn * sizeof(BvhNode) + image_bytes + fs.materials.size() * sizeof(DevMaterial));
+    c->info = scene_info_of(fs);
     c->has_scene = true;
     return RL_OK;
 }

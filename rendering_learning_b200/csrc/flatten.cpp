@@ -424,10 +424,7 @@ struct Flattener {
                     lo[k] = std::fmin(a, b) - ar;
                     hi[k] = std::fmax(a, b) + ar;
                 }
-                if (!in_boundary && ar >= (double)OW_BIG_RADIUS && (int)fs->big_refs.size() < OW_MAX_BIG)
-                    fs->big_refs.push_back(make_ref(REF_SPHERE, idx));  // tested once per ray, outside the LBVH
-                else
-                    emit(lo, hi, make_ref(REF_SPHERE, idx), id);
+                emit(lo, hi, make_ref(REF_SPHERE, idx), id);  // select_big_prims decides later whether it leaves the LBVH
                 return true;
             }
             case RL_OW_QUAD: {

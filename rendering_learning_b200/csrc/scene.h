@@ -24,10 +24,12 @@ __host__ __device__ inline int make_ref(int type, int index) { return (type << 2
 __host__ __device__ inline int ref_type(int ref) { return (ref >> 28) & 7; }
 __host__ __device__ inline int ref_index(int ref) { return ref & 0x0FFFFFFF; }
 
-// OW spheres at least this large (the r = 1000 ground of the cover scene) stay OUT of the LBVH: their box would
-// cover the whole scene, so every ray tests them anyway.  They go on a short "big" list that is tested once per ray
-// before the traversal (which then starts with a finite tmax), with the quadratic evaluated in f64.
+// OW spheres at least this large evaluate their quadratic in f64: seen from near its surface (the r = 1000 ground of the
+// cover scene) r^2 - |perp|^2 cancels ~7 digits, more than f32 has.
 constexpr float OW_BIG_RADIUS = 64.0f;
+// Primitives that are large against the rest of the scene stay OUT of the LBVH (flatten.cpp select_big_prims): their box
+// would cover everything, so every ray tests them anyway.  They go on a short "big" list that is tested once per ray
+// before the traversal, which then starts with a finite tmax.
 constexpr int OW_MAX_BIG = 8;  // more than this and the rest go through the LBVH like any other sphere
 
 // RTC analytic primitive (unit shape + composed, pre-inverted transform). 176 B.

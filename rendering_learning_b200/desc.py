@@ -130,6 +130,15 @@ class SceneDesc:
         self._frozen = d
         return d
 
+    def check(self) -> A.rl_scene_info:
+        """rl_scene_check: validate + flatten on the host (no GPU needed); raises RlError like scene_upload would"""
+        info = A.rl_scene_info()
+        err = C.create_string_buffer(512)
+        rc = A.load_library().rl_scene_check(C.byref(self.freeze()), C.byref(info), err, 512)
+        if rc != A.RL_OK:
+            raise A.RlError(rc, err.value.decode(errors="replace"))
+        return info
+
     def nbytes(self) -> int:
         """Host bytes that cross to the library on rl_scene_upload (for e2e h2d accounting)."""
         self.freeze()

@@ -266,6 +266,7 @@ extern "C" {
 
     pub fn rl_scene_upload(ctx: *mut rl_ctx, scene: *const rl_scene_desc) -> c_int;
     pub fn rl_scene_info_get(ctx: *mut rl_ctx, out: *mut rl_scene_info) -> c_int;
+    pub fn rl_scene_check(scene: *const rl_scene_desc, out: *mut rl_scene_info, err: *mut c_char, err_cap: i32) -> c_int;
     pub fn rl_lbvh_download(ctx: *mut rl_ctx, out: *mut rl_lbvh_host) -> c_int;
 
     pub fn rl_trace_batch(ctx: *mut rl_ctx, rays: *const rl_ray, n: u64, out: *mut rl_hit) -> c_int;
