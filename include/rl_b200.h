@@ -308,7 +308,8 @@ int rl_ow_reduce_device(rl_ctx* ctx, const rl_ow_camera* cam, const void* d_part
 
 /* Cross-GPU dynamic tile queue: ONE 64-bit counter in the exporting ctx's HBM, mapped into the
  * other ranks' processes with CUDA IPC and popped with system-scope atomics over NVLink by the persistent
- * render kernels, 32 work items (pixel x sample-chunk) per warp-aggregated pop — no host in the loop.
+ * render kernels, 32-64 work items (pixel x sample-chunk) per warp-aggregated pop, the next pop prefetched while the
+ * current batch renders — no host in the loop.
  *   owner : rl_queue_export -> 64-byte handle (ship it to the peers), rl_queue_reset before every render
  *   peers : rl_queue_import
  *   all   : rl_render_ow_shared — asynchronous; every rank passes the SAME job list and writes the items it

@@ -7,8 +7,10 @@
 // time, walks its samples in order (so the per-item sum is deterministic) and regenerates a new camera
 // path as soon as its current path dies, so lanes never idle behind a long path in the same warp.  Lanes
 // that run out of samples refill from a global queue with one warp-aggregated atomic (ballot + popc
-// compaction of the requesting lanes).  Partial sums are written per (chunk, pixel) with plain stores and
+// compaction of the requesting lanes).  Partial sums are written per (chunk, pixel) with one 16-byte store and
 // folded in chunk order by k_ow_reduce, so the image is bit-identical for any GPU count / schedule.
+// k_ow_render5 is the production kernel (resumable per-lane traversal, ballot-scheduled node steps / leaf rounds /
+// service rounds, instantiated per primitive mix); k_ow_render (v3) is kept as the A/B baseline of DESIGN.md §4.
 //
 // RNG: Philox4x32-10 keyed by the camera seed, counter = (pixel, absolute sample, bounce, dimension) —
 // statistical parity with the reference's ChaCha8 streams, and absolute sample indices
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
 // run of inner nodes (mean ~5, max over 32 lanes ~20 on the cover scene, which is the measured 10-12 of 32 lanes).  So
 // every iteration is ONE node step for every lane at an inner node; lanes that reach a leaf park, and the leaf test
 // runs for all parked lanes together once `leaf_min` of them wait (or nobody can step).  leaf_min = 32 degenerates to
-// the while-while schedule (v4).  ncu (profiles/r01_ncu_k_ow_render_v4_v5.json): node steps run at 20 instead of 12.5
+// the while-while schedule (v4).  ncu (profiles/r01_ncu_k_ow_render_v4.json, _v5.json): node steps run at 20 instead of 12.5
 // lanes, the whole kernel at 16 instead of 11.3.
 template <bool COUNT, int MINB, int PRIMS>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
