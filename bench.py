@@ -171,7 +171,7 @@ def reference_arm(args, wl_key: str):
     wl = workloads()[wl_key]
     from oracle import oracle as orc
     orc.build()
-    per_step = 8.0 if wl["kind"] == "ow" else 20.0
+    per_step = args.cpu_seconds or (8.0 if wl["kind"] == "ow" else 20.0)
     vals, what, secs, sps = [], "", [], []
     for i in range(args.warmup + args.steps):
         v, s, what, dt = cpu_run(wl, per_step)
@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (invalidates the headline)")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="CPU budget per reference-arm step (default 8 s OW / 20 s RTC)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
