@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
 // runs for all parked lanes together once `leaf_min` of them wait (or nobody can step).  leaf_min = 32 degenerates to
 // the while-while schedule (v4).  ncu (profiles/r01_ncu_k_ow_render_v4.json, _v5.json): node steps run at 20 instead of 12.5
 // lanes, the whole kernel at 16 instead of 11.3.
-template <bool COUNT, int MINB, int PRIMS>
+template <bool COUNT, int MINB, int PRIMS, int OPT = 2>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
                                                           int sys_queue, int qbatch, long long q_guided, int svc_min, int leaf_min) {
@@ -812,7 +812,12 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             const int keep = 32 - n_end - leaf_min;
             int n_in;
             do {
-                if (node >= 0) RL_NODE_STEP()
+                // OPT node steps per ballot (measured, C4 / C5: 1 -> 12.44 / 67.4 ms, 2 -> 12.11 / 64.7, 3 -> 12.39 / 65.6,
+                // 4 -> 12.63 / 65.4: two halve the ballots while a lane that parks after the first step idles one step only)
+#pragma unroll
+                for (int k = 0; k < (OPT < 1 ? 1 : OPT); k++) {
+                    if (node >= 0) RL_NODE_STEP()
+                }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);
         }
@@ -972,8 +977,9 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     //  ncu summaries stay under profiles/.)
     static const int variant = env_int("RL_OW_KERNEL_V", 5);
     static const int minb_env = env_int("RL_OW_MINB", 0);
-    static const int svc_env = env_int("RL_OW_SVC", 0), leaf_min = env_int("RL_OW_LEAF", 12);
-    static const int generic = env_int("RL_OW_GENERIC", 0);  // 1: never pick the spheres-only instantiation
+    static const int svc_env = env_int("RL_OW_SVC", 0), leaf_env = env_int("RL_OW_LEAF", 0);
+    static const int generic = env_int("RL_OW_GENERIC", 0);
+    static const int opt = env_int("RL_OW_OPT", 0);  // experiments: node steps per ballot (2, 3, 4)  // 1: never pick the spheres-only instantiation
     typedef void (*K3)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
     typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
     K3 k3 = nullptr;
@@ -988,6 +994,8 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     // service threshold (profiles/r01_sweep_ow_v5b.log): sphere scenes shade cheaply and prefer fuller service rounds
     // (C4: 12.50 ms at 24 vs 13.25 at 16); with triangles in the leaf rounds 16 is best (C5: 67.0 vs 74.0 at 24)
     const int svc_min = svc_env ? svc_env : (spheres_only ? 24 : 16);
+    // parked lanes per leaf round, with two node steps per ballot: C4 11.9 ms at 6-10 vs 12.2 at 12; C5 64.7 at 10-12 vs 65.5 at 8
+    const int leaf_min = leaf_env ? leaf_env : (spheres_only ? 8 : 12);
     constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
     if (variant == 3 && !extras) {  // v3 predates media / Noise
         k3 = instrumented ? (K3)k_ow_render<true, 1, 4> : (K3)k_ow_render<false, 1, 4>;
