@@ -167,6 +167,100 @@ k_radix_sort(uint64_t* keys_a, int* idx_a, uint64_t* keys_b, int* idx_b, int n) 
     // 8 passes (even) -> the sorted data is back in (keys_a, idx_a)
 }
 
+// 3b. the same stable LSD radix sort across many CTAs, for primitive counts where ONE CTA is the bottleneck (1 M
+// primitives: 28 of the 32 ms of the build).  Per 8-bit pass: per-tile digit histograms -> one exclusive scan over the
+// [digit][tile] table -> each CTA scatters its own tile with exactly the chunk loop of k_radix_sort, starting from its
+// scanned offsets.  Stable, so the result (and everything built on it) is identical to the one-CTA sort and to the host
+// rebuild.
+constexpr int SORT_TILE = 8 * SORT_THREADS;   // keys per CTA
+constexpr int SORT_MULTI_MIN = 16384;         // below this the single launch wins (24 launches of ~4 us each here)
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_hist(const uint64_t* __restrict__ kin, int n, int shift, int nb, int* __restrict__ hist /*[256][nb]*/) {
+    __shared__ int s_h[256];
+    for (int d = threadIdx.x; d < 256; d += SORT_THREADS) s_h[d] = 0;
+    __syncthreads();
+    const int begin = blockIdx.x * SORT_TILE, end = min(n, begin + SORT_TILE);
+    for (int i = begin + threadIdx.x; i < end; i += SORT_THREADS) atomicAdd(&s_h[(int)((kin[i] >> shift) & 255)], 1);
+    __syncthreads();
+    for (int d = threadIdx.x; d < 256; d += SORT_THREADS) hist[d * nb + blockIdx.x] = s_h[d];
+}
+
+// exclusive scan of m ints in place, one CTA, 1024 per round with a running carry
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scan(int* __restrict__ a, int m) {
+    __shared__ int s_w[SORT_WARPS];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < m; c0 += SORT_THREADS) {
+        int i = c0 + tid;
+        int v = i < m ? a[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_w[lane], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < m) a[i] = carry + s_w[warp] + incl - v;
+        __syncthreads();
+        if (tid == SORT_THREADS - 1) s_carry = carry + s_w[warp] + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter(const uint64_t* __restrict__ kin, const int* __restrict__ iin, uint64_t* __restrict__ kout,
+               int* __restrict__ iout, int n, int shift, int nb, const int* __restrict__ offs /*[256][nb], scanned*/) {
+    __shared__ int s_base[256];
+    __shared__ int s_warp[SORT_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int d = tid; d < 256; d += SORT_THREADS) s_base[d] = offs[d * nb + blockIdx.x];
+    __syncthreads();
+    const int begin = blockIdx.x * SORT_TILE, end = min(n, begin + SORT_TILE);
+    for (int c0 = begin; c0 < end; c0 += SORT_THREADS) {
+        for (int d = tid; d < SORT_WARPS * 256; d += SORT_THREADS) (&s_warp[0][0])[d] = 0;
+        __syncthreads();
+        int i = c0 + tid;
+        bool valid = i < end;
+        uint64_t key = valid ? kin[i] : 0;
+        int id = valid ? iin[i] : 0;
+        int digit = (int)((key >> shift) & 255);
+        unsigned act = __ballot_sync(0xffffffffu, valid);
+        int rank = 0;
+        if (valid) {
+            unsigned same = __match_any_sync(act, digit);
+            rank = __popc(same & ((1u << lane) - 1u));
+            if (rank == 0) s_warp[warp][digit] = __popc(same);
+        }
+        __syncthreads();
+        if (valid) {
+            int off = s_base[digit] + rank;
+            for (int w = 0; w < warp; w++) off += s_warp[w][digit];
+            kout[off] = key;
+            iout[off] = id;
+        }
+        __syncthreads();
+        for (int d = tid; d < 256; d += SORT_THREADS) {
+            int t = 0;
+            for (int w = 0; w < SORT_WARPS; w++) t += s_warp[w][d];
+            s_base[d] += t;
+        }
+        __syncthreads();
+    }
+}
+
 // Karras 2012: length of the common prefix of sorted keys i and j (ties broken by position)
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
@@ -292,8 +386,22 @@ cudaError_t lbvh_build(const LbvhBuffers& b, int n, cudaStream_t stream, int* la
     int blocks = (n + 255) / 256;
     k_morton<<<blocks, 256, 0, stream>>>(b.prim_aabb, n, b.bounds, b.keys, b.sorted_prim);
     nl++;
-    k_radix_sort<<<1, SORT_THREADS, 0, stream>>>(b.keys, b.sorted_prim, b.keys_tmp, b.idx_tmp, n);
-    nl++;
+    if (n < SORT_MULTI_MIN) {
+        k_radix_sort<<<1, SORT_THREADS, 0, stream>>>(b.keys, b.sorted_prim, b.keys_tmp, b.idx_tmp, n);
+        nl++;
+    } else {
+        const int nb = (n + SORT_TILE - 1) / SORT_TILE;  // 256 * nb ints of scratch fit the (n - 1)-int refit counters
+        uint64_t *kin = b.keys, *kout = b.keys_tmp;
+        int *iin = b.sorted_prim, *iout = b.idx_tmp;
+        for (int pass = 0; pass < 8; pass++) {
+            k_sort_hist<<<nb, SORT_THREADS, 0, stream>>>(kin, n, pass * 8, nb, b.counters);
+            k_sort_scan<<<1, SORT_THREADS, 0, stream>>>(b.counters, 256 * nb);
+            k_sort_scatter<<<nb, SORT_THREADS, 0, stream>>>(kin, iin, kout, iout, n, pass * 8, nb, b.counters);
+            nl += 3;
+            uint64_t* tk = kin; kin = kout; kout = tk;
+            int* ti = iin; iin = iout; iout = ti;
+        }  // 8 passes (even): the sorted data is back in (keys, sorted_prim)
+    }
     if (n >= 2) {
         k_hierarchy<<<(n - 1 + 255) / 256, 256, 0, stream>>>(b.keys, n, b.left, b.right, b.parent);
         nl++;

@@ -43,7 +43,7 @@ def test_spot_in_cornell_box(ctx, oracle):
     assert ctx.scene_info().n_prims == 6
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 5, 33, 1025, 4097])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 33, 1025, 4097, 16383, 16384, 40000])  # >= 16384: the multi-CTA radix sort
 def test_sizes_and_duplicates(ctx, oracle, n):
     """ragged sizes, identical centroids (key ties broken by position), one-primitive trees"""
     rng = np.random.default_rng(n)
