@@ -598,7 +598,8 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
     for (int i = 0; i < n_jobs; i++) {
         uint64_t px = (uint64_t)(jobs[i].x1 - jobs[i].x0) * (uint64_t)(jobs[i].y1 - jobs[i].y0);
         for (int ck = jobs[i].chunk_begin; ck < jobs[i].chunk_end; ck++) {
-            long long s0 = ((long long)ck * cam->samples_per_pixel) / nc, s1 = ((long long)(ck + 1) * cam->samples_per_pixel) / nc;
+            int s0, s1;
+            ow_chunk_range(cam->samples_per_pixel, nc, ck, &s0, &s1);
             samples += px * (uint64_t)(s1 - s0);
         }
     }

@@ -15,6 +15,22 @@ cudaError_t launch_rtc_render(const DevScene& sc, const rl_rtc_camera* cam, cons
 cudaError_t launch_rtc_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t n, rl_hit* d_hits,
                              Counters* d_counters, bool instrumented, cudaStream_t stream);
 
+// Sample partition of an OW render, a function of spp ALONE (so the image is independent of the schedule and the GPU
+// count): `body` chunks of about equal size, then OW_TAIL_CHUNKS chunks of OW_TAIL_SIZE samples.  Items are popped
+// chunk-major, so the LAST items of a render are the small ones: what the slowest warp still holds when every other
+// warp of every GPU has run dry is a 2-sample item, not an 8-sample one (the load-balancing tail of an 8-GPU step).
+constexpr int OW_TAIL_CHUNKS = 8, OW_TAIL_SIZE = 2;
+__host__ __device__ inline int ow_tail_chunks(int spp) { return spp >= 64 ? OW_TAIL_CHUNKS : 0; }
+__host__ __device__ inline void ow_chunk_range(int spp, int n_chunks, int chunk, int* s0, int* s1) {
+    const int t = ow_tail_chunks(spp), nb = n_chunks - t, body = spp - t * OW_TAIL_SIZE;
+    if (chunk < nb) {
+        *s0 = (int)(((long long)chunk * body) / nb);
+        *s1 = (int)(((long long)(chunk + 1) * body) / nb);
+    } else {
+        *s0 = body + (chunk - nb) * OW_TAIL_SIZE;
+        *s1 = *s0 + OW_TAIL_SIZE;
+    }
+}
 int ow_num_chunks(int spp);
 int ow_image_height(const rl_ow_camera* c);
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,

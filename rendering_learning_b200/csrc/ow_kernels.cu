@@ -466,11 +466,6 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
     return p.depth > 0;  // depth exhausted: the remaining term is black (camera.rs:239-241)
 }
 
-__device__ __forceinline__ void chunk_range(int spp, int n_chunks, int chunk, int* s0, int* s1) {
-    *s0 = (int)(((long long)chunk * spp) / n_chunks);
-    *s1 = (int)(((long long)(chunk + 1) * spp) / n_chunks);
-}
-
 // get_ray (camera.rs:203-230)
 __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, unsigned sample, Path& p) {
     uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
@@ -558,7 +553,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam,
                         x = job.x0 + px;
                         y = job.y0 + py;
                         chunk = job.chunk_begin + ck;
-                        chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                        ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
                         acc = f3(0.0f, 0.0f, 0.0f);
                         has_item = true;
                     }
@@ -722,7 +717,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                     tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
                     if (px < w && py < hgt) {  // padded slots outside the rectangle are simply skipped
                         int x = job.x0 + px, y = job.y0 + py, chunk = job.chunk_begin + ck, s_end;
-                        chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                        ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
                         if (cam.max_depth <= 0) s = s_end;  // depth 0: every sample is black (camera.rs:239-241)
                         pixel = (unsigned)(y * cam.width + x);
                         sm_x[tid] = x;
@@ -891,16 +886,17 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// Samples are cut into chunks of >= 8 (at most 64 chunks): the chunk is the unit of work a lane owns, so it bounds both
-// the load-balancing tail (a 32-sample item was 1.7 ms of lane time, 10 % of an 8-GPU cover-scene step) and the size
-// of the partial-sum buffer (<= 64 frames).  A function of spp alone, so the image stays independent of the schedule.
+// Samples are cut into chunks of >= 8 (at most 64 chunks) plus the small tail chunks of ow_chunk_range (kernels.h): the
+// chunk is the unit of work a lane owns, so it bounds both the load-balancing tail (a 32-sample item was 1.7 ms of lane
+// time, 10 % of an 8-GPU cover-scene step) and the size of the partial-sum buffer (<= 64 frames).
 int ow_num_chunks(int spp) {
     if (spp <= 0) return 1;
     static const int min_chunk = env_int("RL_OW_CHUNK", 8);  // experiments only: every rank must agree
     static const int max_chunks = env_int("RL_OW_MAXCHUNKS", 64);
-    int per_chunk = (spp + max_chunks - 1) / max_chunks;
+    const int t = ow_tail_chunks(spp), body = spp - t * OW_TAIL_SIZE;
+    int per_chunk = (body + (max_chunks - t) - 1) / (max_chunks - t);
     if (per_chunk < min_chunk) per_chunk = min_chunk;
-    return (spp + per_chunk - 1) / per_chunk;
+    return (body + per_chunk - 1) / per_chunk + t;
 }
 
 int ow_image_height(const rl_ow_camera* c) {
