@@ -73,30 +73,7 @@ impl Ctx {
             .iter()
             .map(|(w, h, px)| sys::rl_image { width: *w, height: *h, rgb: px.as_ptr() })
             .collect();
-        let d = sys::rl_scene_desc {
-            abi_version: sys::RL_B200_ABI_VERSION,
-            flavor: scene.flavor,
-            nodes: scene.nodes.as_ptr(),
-            n_nodes: scene.nodes.len() as i32,
-            children: scene.children.as_ptr(),
-            n_children: scene.children.len() as i32,
-            params: scene.params.as_ptr(),
-            n_params: scene.params.len() as i64,
-            roots: scene.roots.as_ptr(),
-            n_roots: scene.roots.len() as i32,
-            materials: scene.materials.as_ptr(),
-            n_materials: scene.materials.len() as i32,
-            textures: scene.textures.as_ptr(),
-            n_textures: scene.textures.len() as i32,
-            images: images.as_ptr(),
-            n_images: images.len() as i32,
-            lights: scene.lights.as_ptr(),
-            n_lights: scene.lights.len() as i32,
-            max_reflection_depth: scene.max_reflection_depth,
-            void_color: scene.void_color,
-            perlins: scene.perlins.as_ptr(),
-            n_perlins: scene.perlins.len() as i32,
-        };
+        let d = scene.desc(&images);
         self.check(unsafe { sys::rl_scene_upload(self.raw, &d) })
     }
 
@@ -113,6 +90,21 @@ impl Ctx {
         let mut st = sys::rl_stats::default();
         self.check(unsafe { sys::rl_render_ow(self.raw, cam, first_sample, out.as_mut_ptr(), &mut st) })?;
         Ok((out, st))
+    }
+
+    /// `rl_render_rtc_u8`: render + `Canvas::ppm`'s 8-bit `translate` on the device (W*H*3 bytes, row-major).
+    pub fn render_rtc_u8(&mut self, cam: &sys::rl_rtc_camera, aa: u32) -> Result<Vec<u8>> {
+        let mut out = vec![0u8; cam.hsize as usize * cam.vsize as usize * 3];
+        self.check(unsafe { sys::rl_render_rtc_u8(self.raw, cam, aa, out.as_mut_ptr(), ptr::null_mut()) })?;
+        Ok(out)
+    }
+
+    /// `rl_render_ow_u8`: render + `pixel_data` / `linear_to_srgb` / `to_u8` on the device.
+    pub fn render_ow_u8(&mut self, cam: &sys::rl_ow_camera, first_sample: u32) -> Result<Vec<u8>> {
+        let h = unsafe { sys::rl_ow_image_height(cam) } as usize;
+        let mut out = vec![0u8; cam.image_width as usize * h * 3];
+        self.check(unsafe { sys::rl_render_ow_u8(self.raw, cam, first_sample, out.as_mut_ptr(), ptr::null_mut()) })?;
+        Ok(out)
     }
 
     pub fn trace_batch(&mut self, rays: &[sys::rl_ray]) -> Result<Vec<sys::rl_hit>> {
@@ -216,6 +208,49 @@ impl SceneBuilder {
         let id = self.textures.len() as i32 - 1;
         self.tex_ids.insert(k, id);
         id
+    }
+
+    /// `rl_scene_check`: validate + flatten on the host only (no GPU needed); what `Ctx::scene_upload` would accept.
+    pub fn check(&self) -> std::result::Result<sys::rl_scene_info, (i32, String)> {
+        let images: Vec<sys::rl_image> =
+            self.images.iter().map(|(w, h, px)| sys::rl_image { width: *w, height: *h, rgb: px.as_ptr() }).collect();
+        let d = self.desc(&images);
+        let mut info = sys::rl_scene_info::default();
+        let mut err = [0 as std::os::raw::c_char; 512];
+        let rc = unsafe { sys::rl_scene_check(&d, &mut info, err.as_mut_ptr(), 512) };
+        if rc == sys::RL_OK {
+            Ok(info)
+        } else {
+            Err((rc, unsafe { CStr::from_ptr(err.as_ptr()) }.to_string_lossy().into_owned()))
+        }
+    }
+
+    /// the `rl_scene_desc` view of this builder; `images` must outlive the returned struct
+    pub fn desc(&self, images: &[sys::rl_image]) -> sys::rl_scene_desc {
+        sys::rl_scene_desc {
+            abi_version: sys::RL_B200_ABI_VERSION,
+            flavor: self.flavor,
+            nodes: self.nodes.as_ptr(),
+            n_nodes: self.nodes.len() as i32,
+            children: self.children.as_ptr(),
+            n_children: self.children.len() as i32,
+            params: self.params.as_ptr(),
+            n_params: self.params.len() as i64,
+            roots: self.roots.as_ptr(),
+            n_roots: self.roots.len() as i32,
+            materials: self.materials.as_ptr(),
+            n_materials: self.materials.len() as i32,
+            textures: self.textures.as_ptr(),
+            n_textures: self.textures.len() as i32,
+            images: images.as_ptr(),
+            n_images: images.len() as i32,
+            lights: self.lights.as_ptr(),
+            n_lights: self.lights.len() as i32,
+            max_reflection_depth: self.max_reflection_depth,
+            void_color: self.void_color,
+            perlins: self.perlins.as_ptr(),
+            n_perlins: self.perlins.len() as i32,
+        }
     }
 
     pub fn add_perlin(&mut self, p: sys::rl_perlin) -> i32 {
