@@ -106,3 +106,65 @@ def test_csg_nesting_is_lowered_to_contiguous_ranges():
                   lights=[rtc.PointLight((0, 5, -5), (1, 1, 1))])
     i = w.lower().check()
     assert i.n_prims == 6 and i.n_bvh_prims == 0
+
+
+# ---- random trees (hypothesis): whatever nesting the caller builds, every leaf is lowered exactly once ------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+def _ow_tree(draw, depth, counter):
+    m = ow.Lambertian(ow.SolidColor((0.5, 0.5, 0.5)))
+    kind = draw(st.integers(0, 5 if depth < 3 else 1))
+    if kind == 0:
+        counter[0] += 1
+        c = tuple(draw(st.floats(-5, 5)) for _ in range(3))
+        return ow.Sphere(ow.Center.Stationary(c), draw(st.floats(0.1, 2.0)), m)
+    if kind == 1:
+        counter[0] += 1
+        return ow.Quad.new((draw(st.floats(-3, 3)), 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0 + draw(st.floats(0, 2)), 0.0), m)
+    if kind == 2:
+        return _ow_tree(draw, depth + 1, counter).translate((draw(st.floats(-2, 2)), 0.5, -1.0))
+    if kind == 3:
+        return _ow_tree(draw, depth + 1, counter).rotate_y(draw(st.floats(-90, 90))).scale(draw(st.floats(0.5, 2.0)))
+    kids = [_ow_tree(draw, depth + 1, counter) for _ in range(draw(st.integers(1, 4)))]
+    return ow.Bvh.new(kids) if kind == 4 else ow.HittableList(kids)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.data())
+def test_random_ow_trees_lower_every_leaf_once(data):
+    counter = [0]
+    world = _ow_tree(data.draw, 0, counter)
+    info = ow.lower_world(world).check()
+    assert info.n_prims + info.n_bvh_prims == counter[0]
+    assert info.n_bvh_nodes == max(info.n_bvh_prims - 1, 0)
+
+
+def _rtc_tree(draw, depth, counter, in_csg):
+    kind = draw(st.integers(0, 7 if depth < 3 else 2))
+    if kind <= 1:
+        counter[0] += 1
+        return [rtc.Sphere, rtc.Cube][kind]()
+    if kind == 2:
+        if in_csg:  # triangles under a Csg are the one unsupported construct
+            counter[0] += 1
+            return rtc.Cylinder(minimum=0.0, maximum=1.0, closed=True)
+        counter[1] += 1
+        return rtc.Triangle.flat([(0, 0, 0), (1, 0, 0), (0, 1 + draw(st.floats(0, 1)), 0)])
+    if kind == 3:
+        return rtc.Transformed.new(_rtc_tree(draw, depth + 1, counter, in_csg), T.translation(draw(st.floats(-2, 2)), 0.0, 1.0))
+    if kind == 4:
+        return rtc.Bounded.new(_rtc_tree(draw, depth + 1, counter, in_csg))
+    if kind == 5:
+        return rtc.Group.new([_rtc_tree(draw, depth + 1, counter, in_csg) for _ in range(draw(st.integers(1, 3)))])
+    return rtc.Csg(_rtc_tree(draw, depth + 1, counter, True), _rtc_tree(draw, depth + 1, counter, True),
+                   draw(st.sampled_from([rtc.CsgOperation.Union, rtc.CsgOperation.Intersection, rtc.CsgOperation.Difference])))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.data())
+def test_random_rtc_trees_lower_every_leaf_once(data):
+    counter = [0, 0]
+    objs = [_rtc_tree(data.draw, 0, counter, False) for _ in range(data.draw(st.integers(1, 3)))]
+    info = rtc.World(objects=objs, lights=[rtc.PointLight((0, 5, -5), (1, 1, 1))]).lower().check()
+    assert (info.n_prims, info.n_bvh_prims) == (counter[0], counter[1])
