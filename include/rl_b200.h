@@ -14,7 +14,8 @@
  *   - all pointers are caller-owned host memory that only has to stay valid for the duration of the call
  *     (except the `*_device` entry points, which take CUDA device pointers of the ctx's device);
  *   - structs are POD, little-endian, natural alignment; matrices are row-major;
- *   - a ctx is used by one caller thread at a time; one ctx drives one GPU;
+ *   - a ctx is used by one caller thread at a time; a ctx from rl_create drives one GPU, a ctx from rl_create_multi
+ *     drives several GPUs of one node from that one thread;
  *   - there is NO CPU fallback: rl_create fails with RL_E_NO_DEVICE when no sm_100 GPU is visible.
  *
  * The scene description is a direct, loss-free image of the reference's own scene types (an object
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 2
+#define RL_B200_ABI_VERSION 3
 
 /* ---- status codes -------------------------------------------------------------------------- */
 enum {
@@ -235,6 +236,15 @@ typedef struct rl_ctx rl_ctx;
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */
 int rl_create(int device_id, rl_ctx** out);
+/* ONE context over n GPUs of one node (n >= 1, distinct device ids), for a caller that is a single process — the way
+ * a Rust `Camera::render` (OW/src/camera.rs:122-124, RTC/src/scene/camera.rs:93) would use a whole HGX box with one
+ * call.  rl_scene_upload replicates the scene on every GPU; rl_render_ow / rl_render_ow_u8 run ONE persistent launch per
+ * GPU whose warps pop (pixel x sample-chunk) items from one counter in GPU 0's HBM (system-scope atomics over NVLink
+ * peer memory) and store finished items straight into GPU 0's partial-sum buffer, which GPU 0 folds; rl_render_rtc /
+ * rl_render_rtc_u8 give each GPU a band of rows that it copies to the caller's buffer itself.  The image is bit-identical
+ * to a 1-GPU render.  Every other entry point acts on GPU 0.  Needs peer access between GPU 0 and the others. */
+int rl_create_multi(const int32_t* device_ids, int32_t n, rl_ctx** out);
+int rl_device_count(const rl_ctx* ctx); /* GPUs behind the ctx: 1, or rl_create_multi's n */
 void rl_destroy(rl_ctx* ctx);
 const char* rl_last_error(const rl_ctx* ctx); /* ctx may be NULL: error of the last failed rl_create */
 int rl_abi_version(void);
@@ -262,6 +272,13 @@ int rl_lbvh_download(rl_ctx* ctx, rl_lbvh_host* out);
 /* RTC: closest hit per `intersect::hit` (RTC/src/scene/intersect.rs:159-168) over `World::intersect`.
  * OW : `world.hit(r, [t_min, inf))` (OW/src/camera.rs:242-247).                                       */
 int rl_trace_batch(rl_ctx* ctx, const rl_ray* rays, uint64_t n, rl_hit* out);
+/* OW only.  The same, for rays that START on a surface (the scattered rays of camera.rs:248-255): self_nodes[i] is the
+ * leaf node ray i starts on, or -1.  The reference relies on f64 and t_min = 1e-10 (camera.rs:242) not to re-hit that
+ * surface at t ~ 0; the f32 device path instead never re-hits the planar primitive a ray starts on and takes only the FAR
+ * root of its own sphere.  OW rays, with or without self nodes, run through the render kernel's own traversal (ready /
+ * done queues, big list at ray start, node steps, leaf rounds): this is the production code path, not a second one.
+ * t_min is the renderer's: 1e-5 * max|origin_k| + 1e-6 in units of the NORMALISED direction. */
+int rl_trace_batch_ex(rl_ctx* ctx, const rl_ray* rays, const int32_t* self_nodes, uint64_t n, rl_hit* out);
 
 /* ---- renders ------------------------------------------------------------------------------------ */
 /* RTC Camera::render (RTC/src/scene/camera.rs:93-124): out_rgb = W*H*3 f32, row-major (width*y + x),
@@ -306,25 +323,40 @@ int rl_render_ow_device(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sam
 int rl_ow_reduce_device(rl_ctx* ctx, const rl_ow_camera* cam, const void* d_partial,
                         void* d_out_rgb_sum, void* stream);
 
-/* Cross-GPU dynamic tile queue: ONE 64-bit counter in the exporting ctx's HBM, mapped into the
- * other ranks' processes with CUDA IPC and popped with system-scope atomics over NVLink by the persistent
- * render kernels, 32-64 work items (pixel x sample-chunk) per warp-aggregated pop, the next pop prefetched while the
- * current batch renders — no host in the loop.
- *   owner : rl_queue_export -> 64-byte handle (ship it to the peers), rl_queue_reset before every render
+/* Cross-GPU dynamic tile queue for ONE PROCESS PER GPU (torchrun-style launches — a single process uses
+ * rl_create_multi instead).  The exporting ctx owns a control block in its HBM with RL_QUEUE_SLOTS independent
+ * {work counter, completion counter} pairs; peers map it with CUDA IPC and their persistent render kernels pop
+ * (pixel x sample-chunk) items from the work counter with system-scope atomics over NVLink, a whole batch per atomic,
+ * the next batch prefetched while the current one renders — no host in the loop.
+ *   owner : rl_queue_export -> 64-byte handle (ship it to the peers); rl_queue_reset(slot) before a render on that slot
  *   peers : rl_queue_import
- *   all   : rl_render_ow_shared — asynchronous; every rank passes the SAME job list and writes the items it
- *           popped into its own d_partial (zero elsewhere), which is then sum-gathered with NCCL. */
+ *   all   : rl_render_ow_shared(slot) — asynchronous; every rank passes the SAME job list.
+ * Two slots let consecutive renders alternate: the owner resets slot (i + 1) % 2 while render i drains slot i % 2, so a
+ * rank launches render i + 1 without waiting for anybody — a late rank simply pops fewer items — and the only rendezvous
+ * left is the one at the end of a render, after which the owner folds.
+ * Fused gather: the owner also exports n_slots partial-sum buffers of bytes_per_slot each; with d_partial == NULL
+ * rl_render_ow_shared stores every finished item straight into the OWNER's buffer of that slot over NVLink (each
+ * [chunk][y][x] entry is written exactly once, by whichever GPU popped it), and the launch is refused when the camera
+ * needs more than bytes_per_slot.  After the end-of-render rendezvous the owner checks rl_queue_completed == the number
+ * of items (a rank that died leaves it short) and folds with rl_ow_reduce_shared. */
+#define RL_QUEUE_SLOTS 2
 int rl_queue_export(rl_ctx* ctx, void* handle64);
 int rl_queue_import(rl_ctx* ctx, const void* handle64);
-int rl_queue_reset(rl_ctx* ctx, void* stream);
-/* Fused gather: the owner also exports its [n_chunks][H][W][4] partial-sum buffer; with d_partial == NULL
- * rl_render_ow_shared stores every finished item straight into the OWNER's HBM over NVLink (each slot is
- * written exactly once, by whichever GPU popped it), so no separate framebuffer collective is needed — only
- * a rendezvous before rl_ow_reduce_device(d_partial = NULL) folds the chunks on the owner. */
-int rl_partial_export(rl_ctx* ctx, uint64_t bytes, void* handle64);
-int rl_partial_import(rl_ctx* ctx, const void* handle64);
+int rl_queue_reset(rl_ctx* ctx, void* stream, int32_t slot);
+int rl_queue_completed(rl_ctx* ctx, void* stream, int32_t slot, uint64_t* items);
+int rl_partial_export(rl_ctx* ctx, uint64_t bytes_per_slot, int32_t n_slots, void* handle64);
+int rl_partial_import(rl_ctx* ctx, const void* handle64, uint64_t bytes_per_slot, int32_t n_slots);
 int rl_render_ow_shared(rl_ctx* ctx, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs,
-                        int32_t n_jobs, void* d_partial, void* stream);
+                        int32_t n_jobs, void* d_partial, void* stream, int32_t slot);
+int rl_ow_reduce_shared(rl_ctx* ctx, const rl_ow_camera* cam, int32_t slot, void* d_out_rgb_sum, void* stream);
+/* work items (pixel x sample-chunk, in padded 8x4 micro-tiles) a job list holds for this camera: what
+ * rl_queue_completed must reach */
+int64_t rl_ow_job_items(const rl_ow_camera* cam, const rl_job* jobs, int32_t n_jobs);
+
+/* Scheduling parameters of the OW render kernel ("ow.variant", "ow.slots", "ow.minb", "ow.ctas_per_sm", "ow.svc_lo",
+ * "ow.exit_min", "ow.leaf_min", "ow.svc_min"; 0 = the measured default).  They change WHEN work is done, never what is
+ * computed: the image is bit-identical for every setting.  Unknown names / out-of-range values: RL_E_INVALID. */
+int rl_set_option(rl_ctx* ctx, const char* name, int32_t value);
 
 /* enable/disable the instrumented (counting) kernel variants; counters cost atomics, so timing runs
  * keep them off and a separate instrumented pass with the same seed fills rl_stats. */

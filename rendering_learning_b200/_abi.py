@@ -11,7 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librl_b200.so")
 
-RL_B200_ABI_VERSION = 2
+RL_B200_ABI_VERSION = 3
+RL_QUEUE_SLOTS = 2
 
 RL_OK = 0
 RL_E_INVALID = -1
@@ -167,6 +168,8 @@ class rl_job(C.Structure):
 _P = C.c_void_p
 SYMBOLS = {
     "rl_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "rl_create_multi": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(_P)]),
+    "rl_device_count": (C.c_int, [_P]),
     "rl_destroy": (None, [_P]),
     "rl_last_error": (C.c_char_p, [_P]),
     "rl_abi_version": (C.c_int, []),
@@ -179,6 +182,7 @@ SYMBOLS = {
     "rl_scene_check": (C.c_int, [C.POINTER(rl_scene_desc), C.POINTER(rl_scene_info), C.c_char_p, C.c_int32]),
     "rl_lbvh_download": (C.c_int, [_P, C.POINTER(rl_lbvh_host)]),
     "rl_trace_batch": (C.c_int, [_P, C.POINTER(rl_ray), C.c_uint64, C.POINTER(rl_hit)]),
+    "rl_trace_batch_ex": (C.c_int, [_P, C.POINTER(rl_ray), C.POINTER(C.c_int32), C.c_uint64, C.POINTER(rl_hit)]),
     "rl_render_rtc": (C.c_int, [_P, C.POINTER(rl_rtc_camera), C.c_uint32, C.POINTER(C.c_float),
                                 C.POINTER(rl_stats)]),
     "rl_render_ow": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(C.c_float),
@@ -196,10 +200,15 @@ SYMBOLS = {
     "rl_set_instrumented": (C.c_int, [_P, C.c_int]),
     "rl_queue_export": (C.c_int, [_P, C.c_void_p]),
     "rl_queue_import": (C.c_int, [_P, C.c_void_p]),
-    "rl_queue_reset": (C.c_int, [_P, _P]),
-    "rl_partial_export": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
-    "rl_partial_import": (C.c_int, [_P, C.c_void_p]),
-    "rl_render_ow_shared": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(rl_job), C.c_int32, _P, _P]),
+    "rl_queue_reset": (C.c_int, [_P, _P, C.c_int32]),
+    "rl_queue_completed": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_uint64)]),
+    "rl_partial_export": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_void_p]),
+    "rl_partial_import": (C.c_int, [_P, C.c_void_p, C.c_uint64, C.c_int32]),
+    "rl_render_ow_shared": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_uint32, C.POINTER(rl_job), C.c_int32, _P, _P,
+                                      C.c_int32]),
+    "rl_ow_reduce_shared": (C.c_int, [_P, C.POINTER(rl_ow_camera), C.c_int32, _P, _P]),
+    "rl_ow_job_items": (C.c_int64, [C.POINTER(rl_ow_camera), C.POINTER(rl_job), C.c_int32]),
+    "rl_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
 }
 
 

@@ -1,4 +1,5 @@
-"""Thin object wrapper over the C ABI (include/rl_b200.h).  One Context = one rl_ctx = one GPU."""
+"""Thin object wrapper over the C ABI (include/rl_b200.h).  One Context = one rl_ctx: one GPU, or — Context([0, 1, ...])
+— several GPUs of one node behind rl_create_multi."""
 from __future__ import annotations
 
 import ctypes as C
@@ -10,10 +11,15 @@ from .desc import SceneDesc
 
 
 class Context:
-    def __init__(self, device_id: int = 0):
+    def __init__(self, device_id=0):
         self.lib = A.load_library()
         h = C.c_void_p()
-        rc = self.lib.rl_create(int(device_id), C.byref(h))
+        if isinstance(device_id, (list, tuple)):
+            ids = (C.c_int32 * len(device_id))(*[int(d) for d in device_id])
+            rc = self.lib.rl_create_multi(ids, len(device_id), C.byref(h))
+            device_id = int(device_id[0]) if len(device_id) else 0
+        else:
+            rc = self.lib.rl_create(int(device_id), C.byref(h))
         if rc != A.RL_OK:
             msg = self.lib.rl_last_error(None)
             raise A.RlError(rc, (msg or b"").decode())
@@ -45,6 +51,13 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.rl_synchronize(self.h))
+
+    def device_count(self) -> int:
+        return int(self.lib.rl_device_count(self.h))
+
+    def set_option(self, name: str, value: int):
+        """Scheduling parameters of the OW kernel (rl_set_option): never change the image."""
+        self._check(self.lib.rl_set_option(self.h, name.encode(), int(value)))
 
     def measure_peaks(self) -> dict:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
@@ -96,7 +109,9 @@ class Context:
         return out
 
     # ---- ray batches -------------------------------------------------------------------------
-    def trace_batch(self, origins, directions, times=None):
+    def trace_batch(self, origins, directions, times=None, self_nodes=None):
+        """closest hits of a ray batch; OW rays run through the render kernel's own traversal.  self_nodes (OW): the
+        leaf node each ray starts on (-1 none), for scattered rays (rl_trace_batch_ex)."""
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
         n = o.shape[0]
@@ -107,6 +122,13 @@ class Context:
             rays[:, 6] = np.asarray(times, np.float32)
         hits = np.zeros(n, dtype=np.dtype([("node", np.int32), ("t", np.float32),
                                            ("u", np.float32), ("v", np.float32)]))
+        if self_nodes is not None:
+            sn = np.ascontiguousarray(self_nodes, np.int32).reshape(-1)
+            assert sn.shape[0] == n
+            self._check(self.lib.rl_trace_batch_ex(self.h, rays.ctypes.data_as(C.POINTER(A.rl_ray)),
+                                                   sn.ctypes.data_as(C.POINTER(C.c_int32)), C.c_uint64(n),
+                                                   hits.ctypes.data_as(C.POINTER(A.rl_hit))))
+            return hits
         self._check(self.lib.rl_trace_batch(self.h, rays.ctypes.data_as(C.POINTER(A.rl_ray)),
                                             C.c_uint64(n),
                                             hits.ctypes.data_as(C.POINTER(A.rl_hit))))
@@ -189,26 +211,38 @@ class Context:
         buf = C.create_string_buffer(handle, 64)
         self._check(self.lib.rl_queue_import(self.h, buf))
 
-    def partial_export(self, nbytes: int) -> bytes:
+    def partial_export(self, bytes_per_slot: int, n_slots: int = A.RL_QUEUE_SLOTS) -> bytes:
         buf = C.create_string_buffer(64)
-        self._check(self.lib.rl_partial_export(self.h, C.c_uint64(nbytes), buf))
+        self._check(self.lib.rl_partial_export(self.h, C.c_uint64(bytes_per_slot), n_slots, buf))
         return buf.raw
 
-    def partial_import(self, handle: bytes):
+    def partial_import(self, handle: bytes, bytes_per_slot: int, n_slots: int = A.RL_QUEUE_SLOTS):
         buf = C.create_string_buffer(handle, 64)
-        self._check(self.lib.rl_partial_import(self.h, buf))
+        self._check(self.lib.rl_partial_import(self.h, buf, C.c_uint64(bytes_per_slot), n_slots))
 
-    def queue_reset(self, stream: int = 0):
-        self._check(self.lib.rl_queue_reset(self.h, C.c_void_p(stream)))
+    def queue_reset(self, stream: int = 0, slot: int = 0):
+        self._check(self.lib.rl_queue_reset(self.h, C.c_void_p(stream), slot))
 
-    def render_ow_shared(self, cam, first_sample, jobs, d_partial_ptr: int, stream: int = 0):
+    def queue_completed(self, stream: int = 0, slot: int = 0) -> int:
+        v = C.c_uint64()
+        self._check(self.lib.rl_queue_completed(self.h, C.c_void_p(stream), slot, C.byref(v)))
+        return int(v.value)
+
+    def ow_job_items(self, cam, jobs) -> int:
+        arr = self._jobs(jobs)
+        return int(self.lib.rl_ow_job_items(C.byref(cam), arr, len(jobs)))
+
+    def render_ow_shared(self, cam, first_sample, jobs, d_partial_ptr: int, stream: int = 0, slot: int = 0):
         arr = self._jobs(jobs)
         self._check(self.lib.rl_render_ow_shared(self.h, C.byref(cam), C.c_uint32(first_sample), arr, len(jobs),
-                                                 C.c_void_p(d_partial_ptr), C.c_void_p(stream)))
+                                                 C.c_void_p(d_partial_ptr), C.c_void_p(stream), slot))
 
     def ow_reduce_device(self, cam, d_partial_ptr: int, d_out_ptr: int, stream: int = 0):
         self._check(self.lib.rl_ow_reduce_device(self.h, C.byref(cam), C.c_void_p(d_partial_ptr),
                                                  C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+    def ow_reduce_shared(self, cam, slot: int, d_out_ptr: int, stream: int = 0):
+        self._check(self.lib.rl_ow_reduce_shared(self.h, C.byref(cam), slot, C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
 
 _default_ctx: Context | None = None

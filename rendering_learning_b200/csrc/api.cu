@@ -63,9 +63,17 @@ struct rl_ctx {
     int upload_launches = 0;
     // work buffers
     DevBuf counters, queue, jobs, prefix, frame, frame8, partial, rays, hits;
+    std::vector<rl_ctx*> group;    // rl_create_multi: [this, peer 1, ...]; empty for a single-GPU ctx
+    cudaEvent_t ev_go = nullptr, ev_done = nullptr;  // group renders: leader's "queue is reset", member's "kernel finished"
+    OwTuning tune;                 // scheduling parameters of the OW kernel (rl_set_option)
+    std::vector<int> node_ref;     // scene node id -> leaf ref (-1: not a leaf), for rl_trace_batch_ex's self nodes
+    DevBuf self_refs;
+    std::vector<DevBuf> job_tables;  // job tables of launches still in flight (> JOBS_INLINE jobs); freed at rl_synchronize
     // cross-GPU queue (CUDA IPC): the owner allocates it, peers map it
     DevBuf shared_queue_own, shared_partial_own;
     float* shared_partial = nullptr;
+    uint64_t shared_partial_bytes = 0;  // bytes per slot behind shared_partial (owner: allocated; peer: told at import)
+    int shared_partial_slots = 0;
     bool shared_partial_imported = false;
     unsigned long long* shared_queue = nullptr;
     bool shared_queue_imported = false;
@@ -170,7 +178,9 @@ int rl_create(int device_id, rl_ctx** out) {
     c->hbm_bytes = prop.totalGlobalMem;
     if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-        (e = c->counters.reserve(sizeof(Counters))) != cudaSuccess || (e = c->queue.reserve(sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = c->counters.reserve(sizeof(Counters))) != cudaSuccess || (e = c->queue.reserve(2 * sizeof(unsigned long long))) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete c;
         return RL_E_CUDA;
@@ -182,6 +192,11 @@ int rl_create(int device_id, rl_ctx** out) {
 
 void rl_destroy(rl_ctx* c) {
     if (!c) return;
+    for (size_t g = 1; g < c->group.size(); g++) {  // a multi-GPU ctx owns its peers
+        c->group[g]->group.clear();
+        rl_destroy(c->group[g]);
+    }
+    c->group.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->shared_queue_imported && c->shared_queue) cudaIpcCloseMemHandle(c->shared_queue);
@@ -192,14 +207,63 @@ void rl_destroy(rl_ctx* c) {
                      &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
-                     &c->jobs, &c->prefix, &c->frame, &c->frame8, &c->partial, &c->rays, &c->hits};
+                     &c->jobs, &c->prefix, &c->frame, &c->frame8, &c->partial, &c->rays, &c->hits, &c->self_refs};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->image_texels) b.release();
+    for (DevBuf& b : c->job_tables) b.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_go) cudaEventDestroy(c->ev_go);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
+
+int rl_create_multi(const int32_t* device_ids, int32_t n, rl_ctx** out) {
+    if (!out || !device_ids || n < 1 || n > 64) {
+        g_create_error = "rl_create_multi: bad arguments";
+        return RL_E_INVALID;
+    }
+    *out = nullptr;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++)
+            if (device_ids[i] == device_ids[j]) {
+                g_create_error = "rl_create_multi: device ids must be distinct";
+                return RL_E_INVALID;
+            }
+    std::vector<rl_ctx*> g;
+    auto undo = [&]() { for (rl_ctx* m : g) rl_destroy(m); };
+    for (int i = 0; i < n; i++) {
+        rl_ctx* m = nullptr;
+        int rc = rl_create(device_ids[i], &m);
+        if (rc != RL_OK) { undo(); return rc; }
+        g.push_back(m);
+    }
+    // every GPU's kernels pop GPU 0's counter and store into GPU 0's partial-sum buffer: peers need access to GPU 0
+    for (int i = 1; i < n; i++) {
+        int can = 0;
+        cudaError_t e = cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[0]);
+        if (e == cudaSuccess && can) {
+            cudaSetDevice(device_ids[i]);
+            e = cudaDeviceEnablePeerAccess(device_ids[0], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        }
+        if (e != cudaSuccess || !can) {
+            char buf[160];
+            snprintf(buf, sizeof(buf), "GPU %d cannot access GPU %d's memory (%s)", device_ids[i], device_ids[0],
+                     e != cudaSuccess ? cudaGetErrorString(e) : "no peer path");
+            g_create_error = buf;
+            undo();
+            return RL_E_CUDA;
+        }
+    }
+    cudaSetDevice(device_ids[0]);
+    if (n > 1) g[0]->group = g;
+    *out = g[0];
+    return RL_OK;
+}
+
+int rl_device_count(const rl_ctx* c) { return !c ? 0 : (c->group.empty() ? 1 : (int)c->group.size()); }
 
 int rl_device_info(rl_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes) {
     if (!c) return RL_E_INVALID;
@@ -215,14 +279,37 @@ int rl_synchronize(rl_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaDeviceSynchronize());  // asynchronous launches may have gone to a caller-provided stream
+    for (DevBuf& b : c->job_tables) b.release();  // nothing is in flight any more
+    c->job_tables.clear();
+    // The overflow counter is STICKY: no entry point zeroes it except the one that reports it (here and read_counters),
+    // so an overflow of an asynchronous launch cannot be wiped by a later call before anyone has seen it.
     Counters h;
     CK(c, cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
     if (h.overflow) {
-        cudaMemset(c->counters.p, 0, sizeof(Counters));
-        c->error = "a traversal stack / work list overflowed on the device";
+        CK(c, cudaMemset(&c->counters.as<Counters>()->overflow, 0, sizeof(h.overflow)));
+        c->error = "a traversal stack / work list overflowed on the device (or a render kernel's watchdog fired)";
         return RL_E_OVERFLOW;
     }
     return RL_OK;
+}
+
+static const struct { const char* name; int OwTuning::*field; int lo, hi; } k_options[] = {
+    {"ow.variant", &OwTuning::variant, 5, 6},        {"ow.slots", &OwTuning::slots, 0, 512},
+    {"ow.minb", &OwTuning::minb, 0, 4},              {"ow.ctas_per_sm", &OwTuning::ctas_per_sm, 0, 8},
+    {"ow.svc_lo", &OwTuning::svc_lo, 0, 32},         {"ow.exit_min", &OwTuning::exit_min, 0, 32},
+    {"ow.leaf_min", &OwTuning::leaf_min, 0, 32},     {"ow.svc_min", &OwTuning::svc_min, 0, 32},
+};
+
+int rl_set_option(rl_ctx* c, const char* name, int32_t value) {
+    if (!c || !name) return RL_E_INVALID;
+    for (const auto& o : k_options) {
+        if (strcmp(o.name, name) != 0) continue;
+        if (value < o.lo || value > o.hi || (o.field == &OwTuning::minb && value != 0 && value != 3 && value != 4))
+            return fail(c, RL_E_INVALID, std::string("option value out of range: ") + name);
+        c->tune.*(o.field) = value;
+        return RL_OK;
+    }
+    return fail(c, RL_E_INVALID, std::string("unknown option: ") + name);
 }
 
 int rl_measure_peaks(rl_ctx* c, double* fp32_tflops, double* l2_gbs, double* hbm_gbs) {
@@ -238,6 +325,8 @@ int rl_set_instrumented(rl_ctx* c, int enabled) {
     return RL_OK;
 }
 
+static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes);
+
 int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     if (!c) return RL_E_INVALID;
     c->has_scene = false;
@@ -245,6 +334,17 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     std::string err;
     int rc = flatten_scene(scene, &fs, &err);
     if (rc != RL_OK) return fail(c, rc, err);
+    rc = upload_flat(c, fs, scene->n_nodes);
+    // a multi-GPU ctx replicates the scene (and builds the LBVH) on every GPU: <= a few MB, bit-identical builds
+    for (size_t g = 1; rc == RL_OK && g < c->group.size(); g++) {
+        rc = upload_flat(c->group[g], fs, scene->n_nodes);
+        if (rc != RL_OK) c->error = c->group[g]->error;
+    }
+    return rc;
+}
+
+static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
+    c->has_scene = false;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     CK(c, cudaEventRecord(c->ev0, s));
@@ -363,6 +463,17 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     d.perlin_vec = c->perlin_vec.as<float4>();
     d.perlin_perm = c->perlin_perm.as<int>();
 
+    // node id -> leaf ref (rl_trace_batch_ex takes the node a ray starts on)
+    c->node_ref.assign((size_t)(n_scene_nodes > 0 ? n_scene_nodes : 0), -1);
+    auto note = [&](int node, int ref) { if (node >= 0 && node < (int)c->node_ref.size()) c->node_ref[node] = ref; };
+    for (size_t i = 0; i < fs.sphere_node.size(); i++) note(fs.sphere_node[i], make_ref(REF_SPHERE, (int)i));
+    for (size_t i = 0; i < fs.quad_node.size(); i++) note(fs.quad_node[i], make_ref(REF_QUAD, (int)i));
+    for (size_t i = 0; i < fs.tri_verts.size(); i++) {
+        int node;
+        memcpy(&node, &fs.tri_verts[i].p1.w, sizeof(int));
+        note(node, make_ref(REF_TRI, (int)i));
+    }
+
     c->info = scene_info_of(fs);
     c->has_scene = true;
     return RL_OK;
@@ -438,16 +549,24 @@ static int make_job_table(rl_ctx* c, const rl_job* jobs, int n_jobs, int width, 
         for (int i = 0; i <= n_jobs; i++) jt->iprefix[i] = prefix[i];
         return RL_OK;
     }
+    // Larger tables get their OWN device buffer per launch (freed at rl_synchronize): a launch on another caller stream may
+    // still be reading the previous table, so the buffer is never reused while anything can be in flight.
     jt->inline_jobs = 0;
-    CK(c, c->jobs.reserve(sizeof(rl_job) * (size_t)n_jobs));
-    CK(c, c->prefix.reserve(sizeof(long long) * (size_t)(n_jobs + 1)));
-    CK(c, cudaStreamSynchronize(s));  // a previous launch on this stream may still read the old table
-    CK(c, cudaMemcpyAsync(c->jobs.p, jobs, sizeof(rl_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(c->prefix.p, prefix.data(), sizeof(long long) * (size_t)(n_jobs + 1), cudaMemcpyHostToDevice, s));
-    CK(c, cudaStreamSynchronize(s));  // `prefix` is a local
-    jt->jobs = c->jobs.as<rl_job>();
-    jt->prefix = c->prefix.as<long long>();
+    c->job_tables.emplace_back();
+    DevBuf& buf = c->job_tables.back();
+    const size_t jb = (sizeof(rl_job) * (size_t)n_jobs + 15) / 16 * 16;
+    CK(c, buf.reserve(jb + sizeof(long long) * (size_t)(n_jobs + 1)));
+    CK(c, cudaMemcpyAsync(buf.p, jobs, sizeof(rl_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync((char*)buf.p + jb, prefix.data(), sizeof(long long) * (size_t)(n_jobs + 1), cudaMemcpyHostToDevice, s));
+    CK(c, cudaStreamSynchronize(s));  // `prefix` is a local; `jobs` is the caller's
+    jt->jobs = reinterpret_cast<const rl_job*>(buf.p);
+    jt->prefix = reinterpret_cast<const long long*>((char*)buf.p + jb);
     return RL_OK;
+}
+
+// zero the statistics counters of a synchronous call, leaving the sticky overflow counter alone
+static cudaError_t reset_stats(rl_ctx* c, cudaStream_t s) {
+    return cudaMemsetAsync(c->counters.p, 0, offsetof(Counters, overflow), s);
 }
 
 static int read_counters(rl_ctx* c, cudaStream_t s, rl_stats* st) {
@@ -462,29 +581,48 @@ static int read_counters(rl_ctx* c, cudaStream_t s, rl_stats* st) {
         st->shades = h.shades;
         st->overflow = h.overflow;
     }
-    if (h.overflow) return fail(c, RL_E_OVERFLOW, "a traversal stack / work list overflowed on the device");
+    if (h.overflow) {
+        CK(c, cudaMemsetAsync(&c->counters.as<Counters>()->overflow, 0, sizeof(h.overflow), s));  // reported: clear
+        return fail(c, RL_E_OVERFLOW, "a traversal stack / work list overflowed on the device");
+    }
     return RL_OK;
 }
 
 extern "C" {
 
-int rl_trace_batch(rl_ctx* c, const rl_ray* rays, uint64_t n, rl_hit* out) {
+int rl_trace_batch_ex(rl_ctx* c, const rl_ray* rays, const int32_t* self_nodes, uint64_t n, rl_hit* out) {
     if (!c || (n > 0 && (!rays || !out))) return RL_E_INVALID;
     if (!c->has_scene) return fail(c, RL_E_NO_SCENE, "no scene uploaded");
     if (n == 0) return RL_OK;
+    if (self_nodes && c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_INVALID, "self nodes apply to OW scenes only");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     CK(c, c->rays.reserve(n * sizeof(rl_ray)));
     CK(c, c->hits.reserve(n * sizeof(rl_hit)));
     CK(c, cudaMemcpyAsync(c->rays.p, rays, n * sizeof(rl_ray), cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    std::vector<int> refs;  // must outlive the asynchronous copy: read_counters below synchronises
+    const int* d_self = nullptr;
+    if (self_nodes) {
+        refs.resize(n);
+        for (uint64_t i = 0; i < n; i++) {
+            const int nd = self_nodes[i];
+            refs[i] = (nd >= 0 && nd < (int)c->node_ref.size()) ? c->node_ref[nd] : -1;
+        }
+        CK(c, c->self_refs.reserve(n * sizeof(int)));
+        CK(c, cudaMemcpyAsync(c->self_refs.p, refs.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+        d_self = c->self_refs.as<int>();
+    }
+    CK(c, reset_stats(c, s));
     if (c->ds.flavor == RL_FLAVOR_RTC)
         CK(c, launch_rtc_trace(c->ds, c->rays.as<rl_ray>(), n, c->hits.as<rl_hit>(), c->counters.as<Counters>(), c->instrumented, s));
     else
-        CK(c, launch_ow_trace(c->ds, c->rays.as<rl_ray>(), n, c->hits.as<rl_hit>(), c->counters.as<Counters>(), c->instrumented, s));
+        CK(c, launch_ow_trace(c->ds, c->rays.as<rl_ray>(), d_self, n, c->hits.as<rl_hit>(), c->queue.as<unsigned long long>(),
+                              c->counters.as<Counters>(), c->instrumented, c->sm_count, s, c->tune));
     CK(c, cudaMemcpyAsync(out, c->hits.p, n * sizeof(rl_hit), cudaMemcpyDeviceToHost, s));
     return read_counters(c, s, nullptr);
 }
+
+int rl_trace_batch(rl_ctx* c, const rl_ray* rays, uint64_t n, rl_hit* out) { return rl_trace_batch_ex(c, rays, nullptr, n, out); }
 
 int rl_render_rtc_device(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, const rl_job* jobs, int32_t n_jobs,
                          void* d_out_rgb, void* stream, rl_stats* stats) {
@@ -505,7 +643,7 @@ int rl_render_rtc_device(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, const
         CK(c, launch_rtc_render(c->ds, cam, inv, aa, jt, (float*)d_out_rgb, c->counters.as<Counters>(), false, s));
         return RL_OK;
     }
-    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    CK(c, reset_stats(c, s));
     CK(c, cudaEventRecord(c->ev0, s));
     CK(c, launch_rtc_render(c->ds, cam, inv, aa, jt, (float*)d_out_rgb, c->counters.as<Counters>(), c->instrumented, s));
     CK(c, cudaEventRecord(c->ev1, s));
@@ -523,9 +661,52 @@ int rl_render_rtc_device(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, const
     return rc;
 }
 
+// RTC on a multi-GPU ctx: the frame is cut into G x JOBS_INLINE interleaved row bands; GPU g renders bands g, g + G, ...
+// with ONE launch and copies them (f32, or 8-bit after the device-side encoder) straight into the caller's buffer, so
+// there is no gather at all.  Pixels are independent and every GPU holds the same scene: bit-identical to one GPU.
+static int group_render_rtc(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, float* out_rgb, uint8_t* out_rgb8, rl_stats* stats) {
+    const int W = cam->hsize, H = cam->vsize, G = (int)c->group.size();
+    int rows = (H + G * JOBS_INLINE - 1) / (G * JOBS_INLINE);
+    rows = (rows + 3) / 4 * 4;  // keep the 8x4 micro-tiles whole
+    const size_t row_px = (size_t)W * 3;
+    rl_stats total{};
+    std::vector<std::vector<rl_job>> bands(G);
+    for (int y0 = 0, k = 0; y0 < H; y0 += rows, k++) bands[k % G].push_back(rl_job{0, y0, W, y0 + rows < H ? y0 + rows : H, 0, 1});
+    for (int g = 0; g < G; g++) {
+        rl_ctx* m = c->group[g];
+        if (bands[g].empty()) continue;
+        CK(c, cudaSetDevice(m->device));
+        CK(c, m->frame.reserve(row_px * H * sizeof(float)));
+        if (out_rgb8) CK(c, m->frame8.reserve(row_px * H));
+        int rc = rl_render_rtc_device(m, cam, aa, bands[g].data(), (int)bands[g].size(), m->frame.p, nullptr, nullptr);  // async
+        if (rc != RL_OK) return fail(c, rc, m->error);
+        for (const rl_job& j : bands[g]) {
+            const size_t off = row_px * j.y0, n = row_px * (size_t)(j.y1 - j.y0);
+            if (out_rgb8) {
+                CK(c, launch_encode_rtc_u8(m->frame.as<float>() + off, m->frame8.as<uint8_t>() + off, n, m->stream));
+                CK(c, cudaMemcpyAsync(out_rgb8 + off, m->frame8.as<uint8_t>() + off, n, cudaMemcpyDeviceToHost, m->stream));
+                total.kernel_launches += 1;
+            } else {
+                CK(c, cudaMemcpyAsync(out_rgb + off, m->frame.as<float>() + off, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+            }
+        }
+        total.kernel_launches += 1;
+    }
+    for (rl_ctx* m : c->group) {
+        int rc = rl_synchronize(m);
+        if (rc != RL_OK) return fail(c, rc, m->error);
+    }
+    CK(c, cudaSetDevice(c->device));
+    total.samples = (uint64_t)W * H * aa * aa;
+    total.upload_ms = c->upload_ms;
+    if (stats) *stats = total;
+    return RL_OK;
+}
+
 int rl_render_rtc(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, float* out_rgb, rl_stats* stats) {
     if (!c || !cam || !out_rgb) return RL_E_INVALID;
     if (cam->hsize < 1 || cam->vsize < 1) return fail(c, RL_E_INVALID, "empty image");
+    if (c->group.size() > 1) return group_render_rtc(c, cam, aa, out_rgb, nullptr, stats);
     size_t bytes = (size_t)cam->hsize * cam->vsize * 3 * sizeof(float);
     CK(c, cudaSetDevice(c->device));
     CK(c, c->frame.reserve(bytes));
@@ -542,6 +723,7 @@ int rl_render_rtc(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, float* out_r
 int rl_render_rtc_u8(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, uint8_t* out_rgb8, rl_stats* stats) {
     if (!c || !cam || !out_rgb8) return RL_E_INVALID;
     if (cam->hsize < 1 || cam->vsize < 1) return fail(c, RL_E_INVALID, "empty image");
+    if (c->group.size() > 1) return group_render_rtc(c, cam, aa, nullptr, out_rgb8, stats);
     size_t n = (size_t)cam->hsize * cam->vsize * 3;
     CK(c, cudaSetDevice(c->device));
     CK(c, c->frame.reserve(n * sizeof(float)));
@@ -561,15 +743,27 @@ int rl_render_rtc_u8(rl_ctx* c, const rl_rtc_camera* cam, uint32_t aa, uint8_t* 
 int rl_ow_image_height(const rl_ow_camera* cam) { return cam ? ow_image_height(cam) : 0; }
 int rl_ow_num_chunks(const rl_ow_camera* cam) { return cam ? ow_num_chunks(cam->samples_per_pixel) : 0; }
 
+// Camera::new's preconditions (OW/src/camera.rs:72-118), shared by every OW render entry point
+static int check_ow_camera(rl_ctx* c, const rl_ow_camera* cam) {
+    if (cam->image_width < 1 || cam->image_width > 65535 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0))
+        return fail(c, RL_E_INVALID, "bad camera parameters");
+    if (ow_image_height(cam) > 65535) return fail(c, RL_E_INVALID, "image taller than 65535 rows");
+    if (cam->max_depth < 0) return fail(c, RL_E_INVALID, "max_depth must be >= 0");
+    double dx = cam->lookfrom[0] - cam->lookat[0], dy = cam->lookfrom[1] - cam->lookat[1], dz = cam->lookfrom[2] - cam->lookat[2];
+    if (dx * dx + dy * dy + dz * dz <= 1e-16) return fail(c, RL_E_INVALID, "cannot normalize vector with magnitude 0");
+    // vup parallel to the view direction: normalize(vup x w) of a zero vector (camera.rs:89)
+    const double* v = cam->vup;
+    double cx = v[1] * dz - v[2] * dy, cy = v[2] * dx - v[0] * dz, cz = v[0] * dy - v[1] * dx;
+    if (cx * cx + cy * cy + cz * cz <= 1e-24 * (dx * dx + dy * dy + dz * dz))
+        return fail(c, RL_E_INVALID, "cannot normalize vector with magnitude 0");
+    return RL_OK;
+}
+
 int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs, int32_t n_jobs,
                         void* d_partial, void* stream, rl_stats* stats) {
     if (!c || !cam || !d_partial) return RL_E_INVALID;
     if (!c->has_scene || c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_NO_SCENE, "no OW scene uploaded");
-    if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0))
-        return fail(c, RL_E_INVALID, "bad camera parameters");
-    if (cam->max_depth < 0) return fail(c, RL_E_INVALID, "max_depth must be >= 0");
-    double dx = cam->lookfrom[0] - cam->lookat[0], dy = cam->lookfrom[1] - cam->lookat[1], dz = cam->lookfrom[2] - cam->lookat[2];
-    if (dx * dx + dy * dy + dz * dz <= 1e-16) return fail(c, RL_E_INVALID, "cannot normalize vector with magnitude 0");
+    if (int rcc = check_ow_camera(c, cam)) return rcc;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
@@ -579,13 +773,13 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
     if (!stats) {
         // asynchronous mode (multi-GPU tile loop): launch and return; errors surface at rl_synchronize
         CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
-                               c->counters.as<Counters>(), false, c->sm_count, s));
+                               c->counters.as<Counters>(), false, c->sm_count, s, false, c->tune));
         return RL_OK;
     }
-    CK(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    CK(c, reset_stats(c, s));
     CK(c, cudaEventRecord(c->ev0, s));
     CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
-                           c->counters.as<Counters>(), c->instrumented, c->sm_count, s));
+                           c->counters.as<Counters>(), c->instrumented, c->sm_count, s, false, c->tune));
     CK(c, cudaEventRecord(c->ev1, s));
     rl_stats st{};
     rc = read_counters(c, s, &st);
@@ -608,10 +802,16 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
     return rc;
 }
 
+// ---- cross-GPU queue, one process per GPU (CUDA IPC) ---------------------------------------------------------------
+// control block: RL_QUEUE_SLOTS x {work counter, completion counter}, 16 bytes per slot
+static unsigned long long* queue_slot(rl_ctx* c, int slot) { return c->shared_queue + 2 * slot; }
+static bool bad_slot(int slot) { return slot < 0 || slot >= RL_QUEUE_SLOTS; }
+
 int rl_queue_export(rl_ctx* c, void* handle64) {
     if (!c || !handle64) return RL_E_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CK(c, cudaSetDevice(c->device));
+    if (c->shared_queue_imported && c->shared_queue) cudaIpcCloseMemHandle(c->shared_queue);
     if (!c->shared_queue_own.p) {
         CK(c, c->shared_queue_own.reserve(256));
         CK(c, cudaMemset(c->shared_queue_own.p, 0, 256));
@@ -627,6 +827,9 @@ int rl_queue_export(rl_ctx* c, void* handle64) {
 int rl_queue_import(rl_ctx* c, const void* handle64) {
     if (!c || !handle64) return RL_E_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->shared_queue_imported && c->shared_queue) cudaIpcCloseMemHandle(c->shared_queue);  // the previous mapping
+    c->shared_queue = nullptr;
+    c->shared_queue_imported = false;
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof(h));
     void* p = nullptr;
@@ -636,80 +839,184 @@ int rl_queue_import(rl_ctx* c, const void* handle64) {
     return RL_OK;
 }
 
-int rl_partial_export(rl_ctx* c, uint64_t bytes, void* handle64) {
-    if (!c || !handle64 || bytes == 0) return RL_E_INVALID;
+int rl_partial_export(rl_ctx* c, uint64_t bytes_per_slot, int32_t n_slots, void* handle64) {
+    if (!c || !handle64 || bytes_per_slot == 0 || n_slots < 1 || n_slots > RL_QUEUE_SLOTS) return RL_E_INVALID;
     CK(c, cudaSetDevice(c->device));
-    CK(c, c->shared_partial_own.reserve(bytes));
+    if (c->shared_partial_imported && c->shared_partial) cudaIpcCloseMemHandle(c->shared_partial);
+    bytes_per_slot = (bytes_per_slot + 255) / 256 * 256;
+    CK(c, c->shared_partial_own.reserve(bytes_per_slot * (uint64_t)n_slots));
     cudaIpcMemHandle_t h;
     CK(c, cudaIpcGetMemHandle(&h, c->shared_partial_own.p));
     memcpy(handle64, &h, sizeof(h));
     c->shared_partial = c->shared_partial_own.as<float>();
+    c->shared_partial_bytes = bytes_per_slot;
+    c->shared_partial_slots = n_slots;
     c->shared_partial_imported = false;
     return RL_OK;
 }
 
-int rl_partial_import(rl_ctx* c, const void* handle64) {
-    if (!c || !handle64) return RL_E_INVALID;
+int rl_partial_import(rl_ctx* c, const void* handle64, uint64_t bytes_per_slot, int32_t n_slots) {
+    if (!c || !handle64 || bytes_per_slot == 0 || n_slots < 1 || n_slots > RL_QUEUE_SLOTS) return RL_E_INVALID;
     CK(c, cudaSetDevice(c->device));
     if (c->shared_partial_imported && c->shared_partial) cudaIpcCloseMemHandle(c->shared_partial);
+    c->shared_partial = nullptr;
+    c->shared_partial_bytes = 0;
+    c->shared_partial_slots = 0;
+    c->shared_partial_imported = false;
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof(h));
     void* p = nullptr;
     CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     c->shared_partial = (float*)p;
+    c->shared_partial_bytes = (bytes_per_slot + 255) / 256 * 256;  // the exporter's geometry: every launch is checked against it
+    c->shared_partial_slots = n_slots;
     c->shared_partial_imported = true;
     return RL_OK;
 }
 
-int rl_queue_reset(rl_ctx* c, void* stream) {
-    if (!c) return RL_E_INVALID;
+int rl_queue_reset(rl_ctx* c, void* stream, int32_t slot) {
+    if (!c || bad_slot(slot)) return RL_E_INVALID;
     if (!c->shared_queue || c->shared_queue_imported) return fail(c, RL_E_INVALID, "only the exporting ctx resets the shared queue");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    CK(c, cudaMemsetAsync(c->shared_queue, 0, sizeof(unsigned long long), s));
+    CK(c, cudaMemsetAsync(queue_slot(c, slot), 0, 2 * sizeof(unsigned long long), s));  // work counter + completion counter
+    return RL_OK;
+}
+
+int rl_queue_completed(rl_ctx* c, void* stream, int32_t slot, uint64_t* items) {
+    if (!c || !items || bad_slot(slot)) return RL_E_INVALID;
+    if (!c->shared_queue || c->shared_queue_imported) return fail(c, RL_E_INVALID, "only the exporting ctx reads the completion counter");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    unsigned long long v = 0;
+    CK(c, cudaMemcpyAsync(&v, queue_slot(c, slot) + 1, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    *items = v;
+    return RL_OK;
+}
+
+int64_t rl_ow_job_items(const rl_ow_camera* cam, const rl_job* jobs, int32_t n_jobs) {
+    if (!cam || n_jobs < 0 || (n_jobs > 0 && !jobs)) return -1;
+    int64_t items = 0;
+    for (int i = 0; i < n_jobs; i++)
+        items += padded_pixels(jobs[i].x1 - jobs[i].x0, jobs[i].y1 - jobs[i].y0) * (int64_t)(jobs[i].chunk_end - jobs[i].chunk_begin);
+    return items;
+}
+
+// the partial-sum buffer of `slot` behind the shared mapping, or an error when this camera does not fit into it
+static int shared_partial_of(rl_ctx* c, const rl_ow_camera* cam, int slot, float** out) {
+    if (!c->shared_partial) return fail(c, RL_E_INVALID, "no partial buffer: pass one or call rl_partial_export / rl_partial_import");
+    if (slot >= c->shared_partial_slots) return fail(c, RL_E_INVALID, "partial-sum slot was not exported");
+    const uint64_t need = (uint64_t)cam->image_width * ow_image_height(cam) * ow_num_chunks(cam->samples_per_pixel) * 16;
+    if (need > c->shared_partial_bytes)
+        return fail(c, RL_E_INVALID, "the shared partial-sum buffer is smaller than width x height x chunks x 16 bytes");
+    *out = reinterpret_cast<float*>(reinterpret_cast<char*>(c->shared_partial) + (size_t)slot * c->shared_partial_bytes);
     return RL_OK;
 }
 
 int rl_render_ow_shared(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, const rl_job* jobs, int32_t n_jobs,
-                        void* d_partial, void* stream) {
-    if (!c || !cam) return RL_E_INVALID;
-    if (!d_partial) d_partial = c->shared_partial;  // fused gather: store straight into the owner's buffer
-    if (!d_partial) return fail(c, RL_E_INVALID, "no partial buffer: pass one or call rl_partial_export / rl_partial_import");
+                        void* d_partial, void* stream, int32_t slot) {
+    if (!c || !cam || bad_slot(slot)) return RL_E_INVALID;
     if (!c->has_scene || c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_NO_SCENE, "no OW scene uploaded");
     if (!c->shared_queue) return fail(c, RL_E_INVALID, "no shared queue: call rl_queue_export / rl_queue_import first");
-    if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0) || cam->max_depth < 0)
-        return fail(c, RL_E_INVALID, "bad camera parameters");
+    if (int rcc = check_ow_camera(c, cam)) return rcc;
+    if (!d_partial) {  // fused gather: store straight into the owner's buffer — which must be large enough for THIS camera
+        float* sp = nullptr;
+        if (int rcc = shared_partial_of(c, cam, slot, &sp)) return rcc;
+        d_partial = sp;
+    }
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
     JobTable jt;
     int rc = make_job_table(c, jobs, n_jobs, cam->image_width, H, nc, true, s, &jt);
     if (rc != RL_OK) return rc;
-    CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->shared_queue, c->counters.as<Counters>(),
-                           false, c->sm_count, s, true));
+    CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, queue_slot(c, slot), c->counters.as<Counters>(),
+                           false, c->sm_count, s, true, c->tune));
     return RL_OK;
 }
 
 int rl_ow_reduce_device(rl_ctx* c, const rl_ow_camera* cam, const void* d_partial, void* d_out, void* stream) {
-    if (c && !d_partial) d_partial = c->shared_partial;
     if (!c || !cam || !d_partial || !d_out) return RL_E_INVALID;
+    if (int rcc = check_ow_camera(c, cam)) return rcc;
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     CK(c, launch_ow_reduce(cam, (const float*)d_partial, (float*)d_out, s));
     return RL_OK;
 }
 
+int rl_ow_reduce_shared(rl_ctx* c, const rl_ow_camera* cam, int32_t slot, void* d_out, void* stream) {
+    if (!c || !cam || !d_out || bad_slot(slot)) return RL_E_INVALID;
+    if (int rcc = check_ow_camera(c, cam)) return rcc;
+    float* sp = nullptr;
+    if (int rcc = shared_partial_of(c, cam, slot, &sp)) return rcc;
+    return rl_ow_reduce_device(c, cam, sp, d_out, stream);
+}
+
+// ---- one process, several GPUs (rl_create_multi) ---------------------------------------------------------------------
+// OW: ONE persistent launch per GPU, all popping the leader's work counter and storing into the leader's partial-sum
+// buffer over NVLink peer memory; CUDA events order "counter reset -> every launch" and "every kernel -> fold".
+static int group_render_ow_partials(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, int H, int nc, rl_stats* st) {
+    rl_job job{0, 0, cam->image_width, H, 0, nc};
+    const int64_t items = rl_ow_job_items(cam, &job, 1);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, reset_stats(c, c->stream));
+    CK(c, cudaMemsetAsync(c->queue.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    CK(c, cudaEventRecord(c->ev_go, c->stream));
+    for (rl_ctx* g : c->group) {
+        CK(c, cudaSetDevice(g->device));
+        CK(c, cudaStreamWaitEvent(g->stream, c->ev_go, 0));
+        JobTable jt;
+        int rc = make_job_table(g, &job, 1, cam->image_width, H, nc, true, g->stream, &jt);
+        if (rc != RL_OK) return rc;
+        CK(c, launch_ow_render(g->ds, cam, first_sample, jt, c->partial.as<float>(), c->queue.as<unsigned long long>(),
+                               g->counters.as<Counters>(), false, g->sm_count, g->stream, true, c->tune));
+        CK(c, cudaEventRecord(g->ev_done, g->stream));
+    }
+    CK(c, cudaSetDevice(c->device));
+    for (rl_ctx* g : c->group) CK(c, cudaStreamWaitEvent(c->stream, g->ev_done, 0));
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    unsigned long long done = 0;
+    CK(c, cudaMemcpyAsync(&done, c->queue.as<unsigned long long>() + 1, sizeof(done), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.0f;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    st->kernel_ms = ms;
+    st->upload_ms = c->upload_ms;
+    st->kernel_launches = (int)c->group.size();
+    st->samples = (uint64_t)cam->image_width * H * (uint64_t)cam->samples_per_pixel;
+    for (rl_ctx* g : c->group) {  // overflow on ANY GPU fails the render
+        Counters h;
+        CK(c, cudaSetDevice(g->device));
+        CK(c, cudaMemcpy(&h, g->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+        if (h.overflow) {
+            cudaMemset(&g->counters.as<Counters>()->overflow, 0, sizeof(h.overflow));
+            st->overflow += h.overflow;
+        }
+    }
+    CK(c, cudaSetDevice(c->device));
+    if (st->overflow) return fail(c, RL_E_OVERFLOW, "a traversal stack / work list overflowed on the device");
+    if ((int64_t)done != items) return fail(c, RL_E_CUDA, "multi-GPU render incomplete: a GPU stored fewer items than it popped");
+    return RL_OK;
+}
+
 // renders into c->frame (sums); shared by rl_render_ow and rl_render_ow_u8
 static int render_ow_to_frame(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sample, rl_stats* st, size_t* frame_bytes) {
-    if (cam->image_width < 1 || cam->samples_per_pixel < 1 || !(cam->aspect_ratio > 0.0))
-        return fail(c, RL_E_INVALID, "bad camera parameters");
+    if (int rcc = check_ow_camera(c, cam)) return rcc;
+    if (!c->has_scene || c->ds.flavor != RL_FLAVOR_OW) return fail(c, RL_E_NO_SCENE, "no OW scene uploaded");
     int H = ow_image_height(cam), nc = ow_num_chunks(cam->samples_per_pixel);
     size_t frame = (size_t)cam->image_width * H * 3 * sizeof(float);
     CK(c, cudaSetDevice(c->device));
     CK(c, c->partial.reserve(frame / 3 * 4 * nc));  // [n_chunks][H][W] float4
     CK(c, c->frame.reserve(frame));
-    rl_job job{0, 0, cam->image_width, H, 0, nc};
-    int rc = rl_render_ow_device(c, cam, first_sample, &job, 1, c->partial.p, nullptr, st);
+    int rc;
+    if (c->group.size() > 1) {
+        rc = group_render_ow_partials(c, cam, first_sample, H, nc, st);
+    } else {
+        rl_job job{0, 0, cam->image_width, H, 0, nc};
+        rc = rl_render_ow_device(c, cam, first_sample, &job, 1, c->partial.p, nullptr, st);
+    }
     if (rc != RL_OK) return rc;
     CK(c, cudaEventRecord(c->ev0, c->stream));
     rc = rl_ow_reduce_device(c, cam, c->partial.p, c->frame.p, nullptr);

@@ -92,11 +92,21 @@ struct RayPre {
     int kx, ky, kz;
     float Sx, Sy, Sz;
 };
+// Reciprocal direction for the slab tests, kept FINITE: with an exactly zero component 1 / d is +-inf and the FMA form
+// of the slab test (centre * inv - o * inv) turns into inf - inf = NaN for every box that straddles the origin's
+// coordinate; fminf / fmaxf drop the NaN and the node is falsely missed (axis-aligned cameras, reflections off
+// axis-aligned quads).  |d_k| < 1e-20 is replaced by +-1e-20: the slab then spans |t| ~ 1e20 x distance, which is
+// "the whole ray" for any coordinate a scene holds, and every product stays far below FLT_MAX.
+__device__ __forceinline__ float safe_rcp(float x) {
+    return 1.0f / (fabsf(x) < 1e-20f ? copysignf(1e-20f, x) : x);
+}
+__device__ __forceinline__ float3 safe_inv(float3 d) { return f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)); }
+
 __device__ __forceinline__ RayPre make_pre(float3 o, float3 d) {
     RayPre r;
     r.o = o;
     r.d = d;
-    r.inv_d = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.inv_d = safe_inv(d);
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
     int kx = kz == 2 ? 0 : kz + 1;
@@ -161,17 +171,14 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
         float4 a = np[0], b = np[1], c = np[2];
         int4 d = *reinterpret_cast<const int4*>(np + 3);
         if (COUNT) lc.nodes++;
-        // slabs of both children
-        float t0x = (a.x - r.o.x) * r.inv_d.x, t1x = (a.w - r.o.x) * r.inv_d.x;
-        float t0y = (a.y - r.o.y) * r.inv_d.y, t1y = (b.x - r.o.y) * r.inv_d.y;
-        float t0z = (a.z - r.o.z) * r.inv_d.z, t1z = (b.y - r.o.z) * r.inv_d.z;
-        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
-        float u0x = (b.z - r.o.x) * r.inv_d.x, u1x = (c.y - r.o.x) * r.inv_d.x;
-        float u0y = (b.w - r.o.y) * r.inv_d.y, u1y = (c.z - r.o.y) * r.inv_d.y;
-        float u0z = (c.x - r.o.z) * r.inv_d.z, u1z = (c.w - r.o.z) * r.inv_d.z;
-        float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));
-        float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));
+        // slabs of both children (scene.h BvhNode: centre + half extent; entry / exit = centre -+ half * |1 / d|)
+        const float aix = fabsf(r.inv_d.x), aiy = fabsf(r.inv_d.y), aiz = fabsf(r.inv_d.z);
+        float c0x = (a.x - r.o.x) * r.inv_d.x, c0y = (a.y - r.o.y) * r.inv_d.y, c0z = (a.z - r.o.z) * r.inv_d.z;
+        float n0 = fmaxf(fmaxf(fmaf(-a.w, aix, c0x), fmaf(-b.x, aiy, c0y)), fmaxf(fmaf(-b.y, aiz, c0z), tmin));
+        float f0 = fminf(fminf(fmaf(a.w, aix, c0x), fmaf(b.x, aiy, c0y)), fminf(fmaf(b.y, aiz, c0z), tmax));
+        float c1x = (b.z - r.o.x) * r.inv_d.x, c1y = (b.w - r.o.y) * r.inv_d.y, c1z = (c.x - r.o.z) * r.inv_d.z;
+        float n1 = fmaxf(fmaxf(fmaf(-c.y, aix, c1x), fmaf(-c.z, aiy, c1y)), fmaxf(fmaf(-c.w, aiz, c1z), tmin));
+        float f1 = fminf(fminf(fmaf(c.y, aix, c1x), fmaf(c.z, aiy, c1y)), fminf(fmaf(c.w, aiz, c1z), tmax));
         // a few ulp of slack keeps the f32 slab test conservative (Ize 2013)
         bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
         if (h0 && d.x < 0) {
@@ -215,54 +222,61 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
     }
 }
 
-// "while-while" traversal (Aila & Laine 2009): the inner loop only descends inner nodes; a lane that reaches a
-// leaf parks until every lane of the warp has one (or is done), then the leaves are tested together.  ncu on the
-// if-if loop above showed primitive tests running with 2-4 of 32 lanes and the pop loop with < 3
-// (profiles/r01_ncu_k_ow_render_v1.json); here the slab tests use the FMA form (lo * inv - o * inv) and the pop
-// is a single predicated stack read — a popped node whose entry distance is now beyond tmax fails its own slab
-// test, so no cull loop is needed.
+// ---- resumable traversal (OW render / trace kernel) --------------------------------------------------------------
 constexpr int TRAV_END = (int)0x80000000;
-template <bool COUNT, class LeafFn>
-__device__ __forceinline__ void bvh_traverse_ww(const BvhNode* __restrict__ nodes, int n_bvh_prims, const RayPre& r,
-                                                float tmin, float tmax, LocalCount<COUNT>& lc, LeafFn leaf) {
-    if (n_bvh_prims <= 0) return;
-    int stack_node[BVH_STACK];
-    int sp = 0;
-    int node = 0;
-    const float3 oi = f3(r.o.x * r.inv_d.x, r.o.y * r.inv_d.y, r.o.z * r.inv_d.z);
-    while (node != TRAV_END) {
-        while (node >= 0) {
-            const float4* np = reinterpret_cast<const float4*>(nodes + node);
-            float4 a = np[0], b = np[1], c = np[2];
-            int4 d = *reinterpret_cast<const int4*>(np + 3);
-            if (COUNT) lc.nodes++;
-            float t0x = fmaf(a.x, r.inv_d.x, -oi.x), t1x = fmaf(a.w, r.inv_d.x, -oi.x);
-            float t0y = fmaf(a.y, r.inv_d.y, -oi.y), t1y = fmaf(b.x, r.inv_d.y, -oi.y);
-            float t0z = fmaf(a.z, r.inv_d.z, -oi.z), t1z = fmaf(b.y, r.inv_d.z, -oi.z);
-            float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-            float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
-            float u0x = fmaf(b.z, r.inv_d.x, -oi.x), u1x = fmaf(c.y, r.inv_d.x, -oi.x);
-            float u0y = fmaf(b.w, r.inv_d.y, -oi.y), u1y = fmaf(c.z, r.inv_d.y, -oi.y);
-            float u0z = fmaf(c.x, r.inv_d.z, -oi.z), u1z = fmaf(c.w, r.inv_d.z, -oi.z);
-            float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));
-            float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));
-            bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
-            int nearc = d.x, farc = d.y;
-            if (n1 < n0) { nearc = d.y; farc = d.x; }
-            if (h0 && h1) {
-                if (sp < BVH_STACK) stack_node[sp++] = farc; else lc.overflow++;
-                node = nearc;
-            } else if (h0 || h1) {
-                node = h0 ? d.x : d.y;
-            } else {
-                node = sp > 0 ? stack_node[--sp] : TRAV_END;
-            }
-        }
-        if (node != TRAV_END) {
-            tmax = leaf(~node, tmax);
-            if (tmax == -RL_INF) return;
-            node = sp > 0 ? stack_node[--sp] : TRAV_END;
-        }
+
+// Per-lane traversal stack: the first SM entries live in shared memory as [entry][thread] (bank = thread, so every
+// push / pop of a warp is ONE conflict-free wavefront whatever the lanes' depths are), deeper entries spill to a local
+// array.  ncu on the all-local stack of round 1: 803 M LDL / STL requests per cover-scene launch, each up to 32
+// wavefronts when the lanes' depths differ, and the pop was the top stall line.
+template <int SM, int THREADS>
+struct TravStack {
+    int* sm;  // this thread's column: sm[entry * THREADS]
+    int loc[BVH_STACK - SM];
+    int sp;
+    __device__ __forceinline__ void init(int* base, int tid) { sm = base + tid; sp = 0; }
+    __device__ __forceinline__ bool push(int v) {
+        if (sp < SM) sm[sp * THREADS] = v;
+        else if (sp < BVH_STACK) loc[sp - SM] = v;
+        else return false;
+        sp++;
+        return true;
+    }
+    __device__ __forceinline__ int pop() {  // TRAV_END when empty
+        if (sp == 0) return TRAV_END;
+        sp--;
+        return sp < SM ? sm[sp * THREADS] : loc[sp - SM];
+    }
+};
+
+// ONE node step of a lane standing at inner node `node`: slab-test both children, step into the nearer hit child and
+// push the other one, or pop.  Boxes are stored as centre + half extent (scene.h), so entry / exit per axis are
+// fma(-+half, |1/d|, fma(centre, 1/d, -o/d)): three FMAs per axis and child and NO per-axis min / max — round 1's
+// lo / hi form spent 20 FMNMX per step on the ALU pipe (61 % busy, the limiter) against 12 FFMA.  A popped node is not
+// culled against the current hit: its children fail their own slab tests.
+template <bool COUNT, class Stack>
+__device__ __forceinline__ void bvh2_step(const BvhNode* __restrict__ nodes, int& node, Stack& st, const float3 inv_d,
+                                          const float3 oi, const float tmin, const float tmax, LocalCount<COUNT>& lc) {
+    const float4* np = reinterpret_cast<const float4*>(nodes + node);
+    const float4 a = np[0], b = np[1], c = np[2];
+    const int2 d = *reinterpret_cast<const int2*>(np + 3);
+    if (COUNT) lc.nodes++;
+    const float aix = fabsf(inv_d.x), aiy = fabsf(inv_d.y), aiz = fabsf(inv_d.z);
+    const float c0x = fmaf(a.x, inv_d.x, -oi.x), c0y = fmaf(a.y, inv_d.y, -oi.y), c0z = fmaf(a.z, inv_d.z, -oi.z);
+    const float n0 = fmaxf(fmaxf(fmaf(-a.w, aix, c0x), fmaf(-b.x, aiy, c0y)), fmaxf(fmaf(-b.y, aiz, c0z), tmin));
+    const float f0 = fminf(fminf(fmaf(a.w, aix, c0x), fmaf(b.x, aiy, c0y)), fminf(fmaf(b.y, aiz, c0z), tmax));
+    const float c1x = fmaf(b.z, inv_d.x, -oi.x), c1y = fmaf(b.w, inv_d.y, -oi.y), c1z = fmaf(c.x, inv_d.z, -oi.z);
+    const float n1 = fmaxf(fmaxf(fmaf(-c.y, aix, c1x), fmaf(-c.z, aiy, c1y)), fmaxf(fmaf(-c.w, aiz, c1z), tmin));
+    const float f1 = fminf(fminf(fmaf(c.y, aix, c1x), fmaf(c.z, aiy, c1y)), fminf(fmaf(c.w, aiz, c1z), tmax));
+    const bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
+    if (h0 && h1) {
+        const bool swap = n1 < n0;
+        if (!st.push(swap ? d.x : d.y)) lc.overflow++;
+        node = swap ? d.y : d.x;
+    } else if (h0 || h1) {
+        node = h0 ? d.x : d.y;
+    } else {
+        node = st.pop();
     }
 }
 

@@ -164,6 +164,10 @@ struct Flattener {
     bool lower_tables() {
         for (int i = 0; i < d->n_textures; i++) {
             const rl_texture& t = d->textures[i];
+            const bool rtc_tex = t.kind >= RL_TEX_RTC_STRIPE && t.kind <= RL_TEX_RTC_RING;
+            const bool ow_tex = t.kind >= RL_TEX_OW_SOLID && t.kind <= RL_TEX_OW_NOISE;
+            if (!(d->flavor == RL_FLAVOR_RTC ? rtc_tex : ow_tex))
+                return fail(RL_E_INVALID, "unknown texture kind (or a kind of the other renderer)");
             DevTexture o{};
             o.a = make_float4((float)t.a[0], (float)t.a[1], (float)t.a[2], as_f(t.kind));
             float inv_scale = t.kind == RL_TEX_OW_CHECKER ? (float)(1.0 / t.scale) : 0.0f;
@@ -201,6 +205,9 @@ struct Flattener {
         }
         for (int i = 0; i < d->n_materials; i++) {
             const rl_material& m = d->materials[i];
+            const bool ow_mat = m.kind >= RL_MAT_OW_LAMBERTIAN && m.kind <= RL_MAT_OW_ISOTROPIC;
+            if (!(d->flavor == RL_FLAVOR_RTC ? m.kind == RL_MAT_RTC_PHONG : ow_mat))
+                return fail(RL_E_INVALID, "unknown material kind (or a kind of the other renderer)");
             DevMaterial o{};
             if (m.texture >= d->n_textures) return fail(RL_E_INVALID, "material texture out of range");
             o.color = make_float4((float)m.color[0], (float)m.color[1], (float)m.color[2], as_f(m.texture));
@@ -540,10 +547,13 @@ struct Flattener {
         }
     }
 
-    bool texture_uses_uv(int tex) {
+    // a checker can nest checkers; the device follows at most 8 levels (tex_value), and a cyclic description must not
+    // recurse forever here
+    bool texture_uses_uv(int tex, int depth = 0) {
+        if (depth > 8) return false;
         const rl_texture& t = d->textures[tex];
         if (t.kind == RL_TEX_OW_IMAGE) return true;
-        if (t.kind == RL_TEX_OW_CHECKER) return texture_uses_uv(t.tex_a) || texture_uses_uv(t.tex_b);
+        if (t.kind == RL_TEX_OW_CHECKER) return texture_uses_uv(t.tex_a, depth + 1) || texture_uses_uv(t.tex_b, depth + 1);
         return false;
     }
 };

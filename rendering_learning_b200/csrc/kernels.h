@@ -31,16 +31,29 @@ __host__ __device__ inline void ow_chunk_range(int spp, int n_chunks, int chunk,
         *s1 = *s0 + OW_TAIL_SIZE;
     }
 }
+// Scheduling parameters of the OW render kernel.  0 = the measured default of the scene's instantiation.  They change
+// WHEN work is done, never what is computed: the image is bit-identical for every setting (tests/test_gpu_ow.py).
+struct OwTuning {
+    int variant = 6;      // 6: CTA-pooled paths (production); 5: round 1's per-lane kernel (kept as the A/B baseline)
+    int slots = 0;        // v6: path slots per CTA (256 .. 512)
+    int minb = 0;         // resident CTAs per SM the kernel is compiled for (3 or 4)
+    int ctas_per_sm = 0;  // launch fewer CTAs per SM than fit
+    int svc_lo = 0;       // v6: a warp with at most this many traversing lanes services a partial batch
+    int exit_min = 0;     // v6: lanes that must finish before the warp leaves the traversal loop to refill
+    int leaf_min = 0;     // parked lanes per leaf round
+    int svc_min = 0;      // v5: lanes that must wait before the warp services them
+};
 int ow_num_chunks(int spp);
 int ow_image_height(const rl_ow_camera* c);
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
                              float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
-                             int sm_count, cudaStream_t stream, bool shared_queue = false);
+                             int sm_count, cudaStream_t stream, bool shared_queue, const OwTuning& tune);
 cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream);
 // 8-bit output encoders (RTC/src/draw/canvas.rs:53-56; OW/src/color.rs:47-57, 130-136), n = W*H*3 channels
 cudaError_t launch_encode_rtc_u8(const float* d_rgb, uint8_t* d_out, size_t n, cudaStream_t stream);
 cudaError_t launch_encode_ow_u8(const float* d_rgb_sum, uint8_t* d_out, size_t n, int samples, cudaStream_t stream);
-cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t n, rl_hit* d_hits, Counters* d_counters,
-                            bool instrumented, cudaStream_t stream);
+cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, const int* d_self_refs, uint64_t n, rl_hit* d_hits,
+                            unsigned long long* d_queue, Counters* d_counters, bool instrumented, int sm_count,
+                            cudaStream_t stream, const OwTuning& tune);
 
 }  // namespace rl

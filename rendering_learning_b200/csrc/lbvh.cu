@@ -328,7 +328,18 @@ __global__ void k_refit(const float* __restrict__ aabb, const int* __restrict__ 
     }
 }
 
-// 6. pack traversal nodes (children's boxes inside the parent)
+// 6. pack traversal nodes (children's boxes inside the parent, as centre + half extent: scene.h BvhNode)
+// centre = fl(0.5 (lo + hi)); half = max(fl(hi - centre), fl(centre - lo)) scaled up by 1 + 2^-21, which covers the
+// rounding of the two subtractions, so [centre - half, centre + half] contains [lo, hi] in exact arithmetic.
+__device__ __forceinline__ void centre_half(const float* box, float* c, float* h) {
+    for (int k = 0; k < 3; k++) {
+        const float lo = box[k], hi = box[3 + k];
+        const float m = __fmul_rn(0.5f, __fadd_rn(lo, hi));
+        const float e = fmaxf(__fsub_rn(hi, m), __fsub_rn(m, lo));
+        c[k] = m;
+        h[k] = __fmul_rn(e, 1.0000005f);
+    }
+}
 __global__ void k_pack(const float* __restrict__ aabb, const int* __restrict__ sorted_prim,
                        const int* __restrict__ prim_ref, int n, const int* __restrict__ left,
                        const int* __restrict__ right, const float* __restrict__ node_aabb,
@@ -336,11 +347,12 @@ __global__ void k_pack(const float* __restrict__ aabb, const int* __restrict__ s
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 1) {
         if (i == 0) {
-            const float* b = aabb;
+            float c[3], h[3];
+            centre_half(aabb, c, h);
             BvhNode nd;
-            nd.a = make_float4(b[0], b[1], b[2], b[3]);
-            nd.b = make_float4(b[4], b[5], FLT_MAX, FLT_MAX);
-            nd.c = make_float4(FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            nd.a = make_float4(c[0], c[1], c[2], h[0]);
+            nd.b = make_float4(h[1], h[2], 0.0f, 0.0f);
+            nd.c = make_float4(0.0f, -1.0f, -1.0f, -1.0f);  // empty second slot: entry > exit for every ray
             nd.d = make_int4(~prim_ref[0], ~prim_ref[0], 0, 0);
             nodes[0] = nd;
         }
@@ -348,7 +360,7 @@ __global__ void k_pack(const float* __restrict__ aabb, const int* __restrict__ s
     }
     if (i >= n - 1) return;
     int ch[2] = {left[i], right[i]};
-    float bx[2][6];
+    float cc[2][3], hh[2][3];
     int id[2];
     for (int c = 0; c < 2; c++) {
         const float* src;
@@ -360,12 +372,12 @@ __global__ void k_pack(const float* __restrict__ aabb, const int* __restrict__ s
             src = node_aabb + 6 * ch[c];
             id[c] = ch[c];
         }
-        for (int k = 0; k < 6; k++) bx[c][k] = src[k];
+        centre_half(src, cc[c], hh[c]);
     }
     BvhNode nd;
-    nd.a = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
-    nd.b = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
-    nd.c = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
+    nd.a = make_float4(cc[0][0], cc[0][1], cc[0][2], hh[0][0]);
+    nd.b = make_float4(hh[0][1], hh[0][2], cc[1][0], cc[1][1]);
+    nd.c = make_float4(cc[1][2], hh[1][0], hh[1][1], hh[1][2]);
     nd.d = make_int4(id[0], id[1], 0, 0);
     nodes[i] = nd;
 }

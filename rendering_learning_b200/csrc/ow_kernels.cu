@@ -15,8 +15,6 @@
 // RNG: Philox4x32-10 keyed by the camera seed, counter = (pixel, absolute sample, bounce, dimension) —
 // statistical parity with the reference's ChaCha8 streams, and absolute sample indices
 // keep render_from_checkpoint streams disjoint like camera.rs:162-170.
-#include <cstdlib>
-
 #include "device.cuh"
 #include "kernels.h"
 
@@ -301,29 +299,6 @@ __device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, flo
     ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, 1.0f, time, self_ref, tmin, h, lc, ray_rnd);
 }
 
-// world.hit(r, [tmin, inf)) through the LBVH (callback form; used by rl_trace_batch and the v1 kernel).
-template <bool COUNT, int TRAV = 0>
-__device__ __forceinline__ OwHit ow_closest(const DevScene& sc, float3 o, float3 d, float time, int self_ref, float tmin,
-                                            LocalCount<COUNT>& lc) {
-    OwHit h;
-    h.t = RL_INF;
-    h.ref = -1;
-    h.b1 = h.b2 = 0.0f;
-    if (COUNT) lc.rays++;
-    RayPre pre = make_pre(o, d);
-    const float a_dd = dot(d, d);
-    OwHit* hp = &h;
-    LocalCount<COUNT>& lcr = lc;
-    auto leaf = [&](int ref, float tmax) -> float {
-        ow_leaf_test<COUNT>(sc, ref, pre, a_dd, time, self_ref, tmin, *hp, lcr);
-        return hp->t;
-    };
-    for (int k = 0; k < sc.n_big; k++) leaf(sc.big_refs[k], h.t);  // OW_BIG_RADIUS spheres live outside the LBVH
-    if (TRAV == 1) bvh_traverse_ww<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, h.t, lc, leaf);
-    else bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, tmin, h.t, lc, leaf);
-    return h;
-}
-
 // state of one path (per lane)
 struct Path {
     float3 o, d;
@@ -341,13 +316,6 @@ __device__ __forceinline__ float ow_tmin(const Path& p) {
 template <bool COUNT, int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, Path& p, const OwHit& h, uint4 rnd,
                                          float3& rad, LocalCount<COUNT>& lc);
-
-template <bool COUNT, int TRAV>
-__device__ __forceinline__ bool ow_bounce(const DevScene& sc, const OwCam& cam, Path& p, uint4 rnd, float3& rad,
-                                          LocalCount<COUNT>& lc) {
-    OwHit h = ow_closest<COUNT, TRAV>(sc, p.o, p.d, p.time, p.self_ref, ow_tmin(p), lc);
-    return ow_shade<COUNT>(sc, cam, p, h, rnd, rad, lc);
-}
 
 // hit record + emitted + scatter for the closest hit `h` of path `p` (camera.rs:246-258).  Returns false when the path
 // ends; `rad` is then the sample's colour.  (Only terminal events add radiance — a miss adds the background, a
@@ -492,105 +460,6 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
     p.self_ref = -1;
 }
 
-template <bool COUNT, int TRAV, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_ow_render(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
-                                                   unsigned long long* __restrict__ queue, Counters* counters, int sys_queue, int qbatch) {
-    LocalCount<COUNT> lc;
-    const unsigned lane = threadIdx.x & 31;
-    const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
-    // lane state
-    bool has_item = false, alive = false, done = false;
-    int x = 0, y = 0, chunk = 0, s = 0, s_end = 0;
-    float3 acc = f3(0.0f, 0.0f, 0.0f);
-    Path p;
-    p.depth = 0;
-    // warp-uniform queue state: the current reserved batch and the prefetched next one
-    long long cur_next = 0, cur_end = 0;
-    bool q_dry = false;
-    unsigned long long next_base = 0;
-    if (lane == 0) next_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
-                                         : atomicAdd(queue, (unsigned long long)qbatch);
-    while (true) {
-        // ---- retire finished items, refill idle lanes (warp-aggregated queue pop) ----
-        if (has_item && !alive && s == s_end) {
-            size_t idx = ((size_t)chunk * cam.height + y) * cam.width + x;
-            reinterpret_cast<float4*>(partial)[idx] = make_float4(acc.x, acc.y, acc.z, 0.0f);  // one 16-byte store
-            has_item = false;
-        }
-        bool need = !has_item && !done;
-        unsigned mask = __ballot_sync(0xffffffffu, need);
-        if (mask) {
-            // The warp owns a reserved batch [cur_next, cur_end) and a PREFETCHED next batch whose atomic was issued
-            // one batch ago, so the round trip to the counter (one ONE counter in rank 0's HBM when sys_queue is
-            // set: CUDA IPC mapping popped over NVLink — a dynamic tile queue with no host in the loop) overlaps
-            // rendering instead of stalling the warp at every pop.
-            if (cur_next >= cur_end && !q_dry) {
-                unsigned long long base = __shfl_sync(0xffffffffu, next_base, 0);
-                cur_next = (long long)base;
-                cur_end = cur_next + qbatch < jt.n_items ? cur_next + qbatch : jt.n_items;
-                if (cur_next >= jt.n_items) {
-                    q_dry = true;
-                    cur_end = cur_next;
-                } else if (lane == 0) {
-                    next_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
-                                          : atomicAdd(queue, (unsigned long long)qbatch);
-                }
-            }
-            long long avail = cur_end - cur_next;
-            int rank_in = __popc(mask & ((1u << lane) - 1u));
-            if (need) {
-                if (rank_in < avail) {
-                    long long item = cur_next + rank_in;
-                    int j = find_job(jt, item);
-                    rl_job job = jt_job(jt, j);
-                    long long local = item - jt_prefix(jt, j);
-                    int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
-                    long long pp = padded_pixels(w, hgt);
-                    int ck = (int)(local / pp);
-                    int px, py;
-                    tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
-                    if (px < w && py < hgt) {  // padded slots outside the rectangle are simply skipped
-                        x = job.x0 + px;
-                        y = job.y0 + py;
-                        chunk = job.chunk_begin + ck;
-                        ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
-                        acc = f3(0.0f, 0.0f, 0.0f);
-                        has_item = true;
-                    }
-                } else if (q_dry) {
-                    done = true;
-                }
-            }
-            int taken = __popc(mask);
-            cur_next += taken < avail ? taken : avail;
-        }
-        if (__all_sync(0xffffffffu, done && !has_item)) break;
-        // ---- path regeneration ----
-        if (has_item && !alive && s < s_end) {
-            if (cam.max_depth <= 0) {
-                s = s_end;  // depth 0: every sample is black (camera.rs:239-241)
-            } else {
-                ow_camera_ray(cam, x, y, (unsigned)(cam.first_sample + s), p);
-                alive = true;
-            }
-        }
-        // ---- one bounce for every live lane ----
-        if (alive) {
-            unsigned pixel = (unsigned)(y * cam.width + x);
-            unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
-            uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
-            float3 rad;
-            bool cont = ow_bounce<COUNT, TRAV>(sc, cam, p, rnd, rad, lc);
-            if (!cont) {
-                acc = acc + rad;  // samples are folded in order (camera.rs:174)
-                alive = false;
-                s++;
-            }
-        }
-    }
-    lc.flush(counters);
-}
-
 // ---- v4: resumable traversal + threshold-triggered service ---------------------------------------------------------
 // ncu on v3 (profiles/r01_ncu_k_ow_render_v3.json, r01_ncu_ow_c5.json): 10.8 of 32 lanes per issued instruction on the
 // cover scene and 6.3 on the Cornell box — a bounce (traversal + shade) ends only when the slowest lane's traversal
@@ -629,8 +498,9 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     Path p;
     p.depth = 0;
     // traversal (resumable)
-    int node = TRAV_END, sp = 0;
-    int stack_node[BVH_STACK];
+    int node = TRAV_END;
+    TravStack<0, 256> st;  // all-local stack: the round-1 baseline the v6 kernel is measured against
+    st.init(nullptr, 0);
     float3 inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
     float tmin = 0.0f;
     TriShear shear;
@@ -749,14 +619,14 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             // unit direction: t is internal to this kernel (hit point = o + d t either way), and with |d| = 1 the
             // sphere quadratic, the medium's ray length and the tmin scale lose their divisions by d.d
             p.d = p.d * rsqrtf(dot(p.d, p.d));
-            inv_d = f3(1.0f / p.d.x, 1.0f / p.d.y, 1.0f / p.d.z);
+            inv_d = safe_inv(p.d);
             oi = p.o * inv_d;
             tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // ow_tmin with |d| = 1
             if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
             if (PRIMS & PRIMS_MEDIA)
                 ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
-            sp = 0;
+            st.sp = 0;
             if (COUNT) lc.rays++;
             for (int k = 0; k < sc.n_big; k++)  // the big list: once per ray, here, with the serviced lanes
                 ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc, ray_rnd);
@@ -766,40 +636,11 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
         if (m_done == FULL) break;
         // ================= traversal: until svc_min lanes wait for service =================
         const int n_done = __popc(m_done);
-#define RL_NODE_STEP()                                                                                              \
-    {                                                                                                               \
-        const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);                                        \
-        float4 a = np[0], b = np[1], c = np[2];                                                                     \
-        int4 d = *reinterpret_cast<const int4*>(np + 3);                                                            \
-        if (COUNT) lc.nodes++;                                                                                      \
-        const float tmax = hit.t;                                                                                   \
-        float t0x = fmaf(a.x, inv_d.x, -oi.x), t1x = fmaf(a.w, inv_d.x, -oi.x);                                     \
-        float t0y = fmaf(a.y, inv_d.y, -oi.y), t1y = fmaf(b.x, inv_d.y, -oi.y);                                     \
-        float t0z = fmaf(a.z, inv_d.z, -oi.z), t1z = fmaf(b.y, inv_d.z, -oi.z);                                     \
-        float n0 = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));                    \
-        float f0 = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));                    \
-        float u0x = fmaf(b.z, inv_d.x, -oi.x), u1x = fmaf(c.y, inv_d.x, -oi.x);                                     \
-        float u0y = fmaf(b.w, inv_d.y, -oi.y), u1y = fmaf(c.z, inv_d.y, -oi.y);                                     \
-        float u0z = fmaf(c.x, inv_d.z, -oi.z), u1z = fmaf(c.w, inv_d.z, -oi.z);                                     \
-        float n1 = fmaxf(fmaxf(fminf(u0x, u1x), fminf(u0y, u1y)), fmaxf(fminf(u0z, u1z), tmin));                    \
-        float f1 = fminf(fminf(fmaxf(u0x, u1x), fmaxf(u0y, u1y)), fminf(fmaxf(u0z, u1z), tmax));                    \
-        bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);                                                            \
-        int nearc = d.x, farc = d.y;                                                                                \
-        if (n1 < n0) { nearc = d.y; farc = d.x; }                                                                   \
-        if (h0 && h1) {                                                                                             \
-            if (sp < BVH_STACK) stack_node[sp++] = farc; else lc.overflow++;                                        \
-            node = nearc;                                                                                           \
-        } else if (h0 || h1) {                                                                                      \
-            node = h0 ? d.x : d.y;                                                                                  \
-        } else {                                                                                                    \
-            node = sp > 0 ? stack_node[--sp] : TRAV_END;                                                            \
-        }                                                                                                           \
-    }
         while (true) {
             // leaf round: every lane parked at a leaf tests it and pops
             if (node < 0 && node != TRAV_END) {
                 ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc, ray_rnd);
-                node = sp > 0 ? stack_node[--sp] : TRAV_END;
+                node = st.pop();
             }
             const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));
             if (n_end == 32 || n_end - n_done >= svc_min) break;
@@ -811,12 +652,469 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 // 4 -> 12.63 / 65.4: two halve the ballots while a lane that parks after the first step idles one step only)
 #pragma unroll
                 for (int k = 0; k < (OPT < 1 ? 1 : OPT); k++) {
-                    if (node >= 0) RL_NODE_STEP()
+                    if (node >= 0) bvh2_step<COUNT>(sc.nodes, node, st, inv_d, oi, tmin, hit.t, lc);
                 }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);
         }
-#undef RL_NODE_STEP
+    }
+    lc.flush(counters);
+}
+
+// ---- v6: CTA-pooled paths — ready / done queues in shared memory, any warp traverses, any warp services ---------------
+// ncu on v5 (profiles/r01_ncu_k_ow_render5_c4_500spp.json): 17 of 32 lanes per issued instruction.  The loss is
+// structural: a warp's lanes are in one of three states (inner node, leaf, waiting for service) and only one state
+// runs at a time; with the measured-best service threshold of 24, about 12 lanes idle through the node steps, and the
+// service round itself runs at ~10 lanes because materials diverge.  v6 takes the path OUT of the lane:
+//   * a CTA owns P path slots in shared memory (SoA, [word][slot]): ray, throughput, item bookkeeping, hit record;
+//   * a lane that finishes its traversal writes the hit into the slot, pushes the slot id on the DONE ring and takes the
+//     next ray from the READY ring at once (ballot / popc compaction, one shared-memory atomic per warp and ring), so
+//     node steps run with nearly full warps whatever the other lanes' rays do;
+//   * any warp that finds 32 ids on the DONE ring services them as ONE full batch (hit record + emitted + scatter,
+//     retire, item refill from the global queue, camera-ray regeneration, big-list test) and pushes the new rays on the
+//     READY ring.  Nothing ever waits for another warp to do a particular thing: every warp does whatever work exists.
+// This is north_star's wavefront (stages separated by queues, warp-level compaction) at CTA scope: the queues hold
+// 4-byte slot ids and never leave shared memory, where a global wavefront round-trips 128 B per ray-bounce through L2 /
+// HBM.  Per-lane arithmetic — leaf tests, shading, RNG counters, the order samples are folded in — is
+// v5's, so the image is bit-identical to v5's for any schedule (tests/test_gpu_ow.py).
+// MODE_TRACE runs caller-supplied rays through the SAME queues, refill, big-list start, node steps and leaf rounds and
+// writes rl_hit records: rl_trace_batch is the production traversal, not a second implementation.
+namespace v6 {
+constexpr int THREADS = 256, QCAP = 512, STACK_SM = 8, EMPTY = -1;
+constexpr int MODE_RENDER = 0, MODE_TRACE = 1;
+// slot words
+enum { OX, OY, OZ, DX, DY, DZ, TIME, SELF, HT, HREF, THRX, THRY, THRZ, DEPTH, XY, S, SEND, CHUNK, ACCX, ACCY, ACCZ, FLAGS, N_BASE };
+constexpr int HB1 = N_BASE, HB2 = N_BASE + 1, RND = N_BASE + 2;
+__host__ __device__ constexpr int slot_words(int prims) {
+    return (prims & PRIMS_MEDIA) ? N_BASE + 3 : ((prims & (PRIMS_TRIS | PRIMS_QUADS)) ? N_BASE + 2 : N_BASE);
+}
+__host__ __device__ constexpr size_t smem_bytes(int prims, int P) {
+    return (size_t)slot_words(prims) * P * 4 + (size_t)STACK_SM * THREADS * 4 + 2 * (size_t)QCAP * 4;
+}
+
+struct Ctl {
+    volatile unsigned r_head, r_tail, d_head, d_tail;  // READY / DONE rings
+    volatile int live, abort;                         // slots not yet dead; watchdog
+    volatile int it_lock, it_dry, nx_size;            // CTA-level item batch (reserved from the global queue)
+    volatile long long it_next, it_end;
+    volatile unsigned long long nx_base;              // prefetched next batch (its atomic was issued one batch ago)
+};
+
+struct TraceIO {
+    const rl_ray* rays;
+    const int* self_refs;  // optional: the leaf ref each ray starts on (-1 none)
+    rl_hit* hits;
+};
+
+__device__ __forceinline__ void ring_push(int* ring, volatile unsigned* tail, unsigned mask, bool pred, int id, unsigned lane) {
+    if (!mask) return;
+    const int n = __popc(mask), leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd((unsigned*)tail, (unsigned)n);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) {
+        volatile int* e = ring + ((base + __popc(mask & ((1u << lane) - 1u))) & (QCAP - 1));
+        while (*e != EMPTY) {}  // a consumer that reserved this entry a whole lap ago has not read it yet (never seen; kept for safety)
+        *e = id;
+    }
+    __syncwarp();
+}
+
+// up to popc(mask) ids for the lanes in `mask`; -1 for lanes that got none
+__device__ __forceinline__ int ring_pop(int* ring, volatile unsigned* head, volatile unsigned* tail, unsigned mask, bool pred,
+                                        unsigned lane) {
+    if (!mask) return -1;
+    const int want = __popc(mask), leader = __ffs(mask) - 1;
+    unsigned h = 0;
+    int got = 0;
+    if ((int)lane == leader) {
+        h = *head;
+        while (true) {
+            const int avail = (int)(*tail - h);
+            got = avail < want ? avail : want;
+            if (got <= 0) { got = 0; break; }
+            const unsigned old = atomicCAS((unsigned*)head, h, h + (unsigned)got);
+            if (old == h) break;
+            h = old;
+        }
+    }
+    got = __shfl_sync(0xffffffffu, got, leader);
+    h = __shfl_sync(0xffffffffu, h, leader);
+    int id = -1;
+    if (pred) {
+        const int r = __popc(mask & ((1u << lane) - 1u));
+        if (r < got) {
+            volatile int* e = ring + ((h + (unsigned)r) & (QCAP - 1));
+            while ((id = *e) == EMPTY) {}  // the producer bumped the tail and writes the entry right after
+            *e = EMPTY;
+        }
+    }
+    __threadfence_block();  // slot data written before the id was pushed is visible from here on
+    __syncwarp();
+    return id;
+}
+
+// `n` work items for one service batch, out of the CTA's reserved batch of the global queue (one lane calls).  The next
+// batch's global atomic (system scope over NVLink when the counter is rank 0's) was issued when the current one was
+// installed, so its round trip overlaps a whole batch of rendering.  Returns how many were granted from *start on.
+__device__ __forceinline__ int items_take(Ctl& ctl, int n, long long n_items, unsigned long long* queue, int sys_queue, int qbatch,
+                                          long long q_guided, long long* start, int* dry) {
+    while (atomicCAS((int*)&ctl.it_lock, 0, 1) != 0) __nanosleep(32);
+    __threadfence_block();
+    long long nx = ctl.it_next, en = ctl.it_end;
+    int isdry = ctl.it_dry;
+    if (nx >= en && !isdry) {
+        nx = (long long)ctl.nx_base;
+        const int got = ctl.nx_size;
+        en = nx + got < n_items ? nx + got : n_items;
+        if (nx >= n_items) {
+            isdry = 1;
+            en = nx;
+            ctl.it_dry = 1;
+        } else {
+            // guided self-scheduling: full batches while the queue is long, small ones near its end
+            const int want = n_items - nx > q_guided ? qbatch : 32;
+            ctl.nx_size = want;
+            ctl.nx_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)want) : atomicAdd(queue, (unsigned long long)want);
+        }
+        ctl.it_end = en;
+    }
+    const long long avail = en - nx;
+    const int take = (long long)n < avail ? n : (int)avail;
+    *start = nx;
+    ctl.it_next = nx + take;
+    *dry = isdry;
+    __threadfence_block();
+    atomicExch((int*)&ctl.it_lock, 0);
+    return take;
+}
+}  // namespace v6
+
+template <bool COUNT, int MINB, int PRIMS, int MODE>
+__global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
+                                                          unsigned long long* __restrict__ queue, Counters* counters,
+                                                          int sys_queue, int qbatch, long long q_guided, int P, int svc_lo,
+                                                          int exit_min, int leaf_min, v6::TraceIO tio) {
+    using namespace v6;
+    constexpr bool HAS_B = (PRIMS & (PRIMS_TRIS | PRIMS_QUADS | PRIMS_MEDIA)) != 0;
+    constexpr int NW = slot_words(PRIMS);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* const pool = reinterpret_cast<float*>(smem_raw);
+    int* const pooli = reinterpret_cast<int*>(smem_raw);
+    int* const stack_base = pooli + NW * P;
+    int* const ring_r = stack_base + STACK_SM * THREADS;
+    int* const ring_d = ring_r + QCAP;
+    __shared__ Ctl ctl;
+#define SL(w, id) pool[(w) * P + (id)]
+#define SLI(w, id) pooli[(w) * P + (id)]
+    LocalCount<COUNT> lc;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
+    const long long n_items = jt.n_items;
+    // every slot starts on the DONE ring with no item: the first service rounds hand out the first items
+    for (int i = tid; i < QCAP; i += THREADS) {
+        ring_r[i] = EMPTY;
+        ring_d[i] = i < P ? i : EMPTY;
+    }
+    for (int i = tid; i < P; i += THREADS) {
+        SLI(CHUNK, i) = -1;
+        SLI(FLAGS, i) = 0;
+    }
+    if (tid == 0) {
+        ctl.r_head = ctl.r_tail = 0;
+        ctl.d_head = 0;
+        ctl.d_tail = (unsigned)P;
+        ctl.live = P;
+        ctl.abort = 0;
+        ctl.it_lock = 0;
+        ctl.it_dry = 0;
+        ctl.it_next = ctl.it_end = 0;
+        ctl.nx_size = qbatch;
+        ctl.nx_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch) : atomicAdd(queue, (unsigned long long)qbatch);
+    }
+    __syncthreads();
+
+    // ---- lane state: the ray this lane is traversing ----
+    int slot = -1, node = TRAV_END;
+    TravStack<STACK_SM, THREADS> st;
+    st.init(stack_base, tid);
+    float3 o = f3(0.0f, 0.0f, 0.0f), d = f3(0.0f, 0.0f, 1.0f), inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
+    float tmin = 0.0f, time = 0.0f;
+    int self_ref = -1;
+    TriShear shear;
+    shear.k = 0; shear.Sx = shear.Sy = shear.Sz = 0.0f;
+    unsigned ray_rnd = 0u;
+    OwHit hit;
+    hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
+    unsigned spins = 0, retired = 0;
+
+    while (true) {
+        // ================= (A) lanes whose traversal ended: hit record into the slot, slot id onto the DONE ring =================
+        const bool fin = slot >= 0 && node == TRAV_END;
+        if (fin) {
+            SL(HT, slot) = hit.t;
+            SLI(HREF, slot) = hit.ref;
+            if (HAS_B) {
+                SL(HB1, slot) = hit.b1;
+                SL(HB2, slot) = hit.b2;
+            }
+        }
+        const unsigned m_fin = __ballot_sync(FULL, fin);
+        if (m_fin) {
+            __threadfence_block();
+            ring_push(ring_d, &ctl.d_tail, m_fin, fin, slot, lane);
+            if (fin) slot = -1;
+        }
+        // ================= (B) idle lanes take the next ray from the READY ring =================
+        const unsigned m_idle = __ballot_sync(FULL, slot < 0);
+        if (m_idle) {
+            const int got = ring_pop(ring_r, &ctl.r_head, &ctl.r_tail, m_idle, slot < 0, lane);
+            if (got >= 0) {
+                slot = got;
+                o = f3(SL(OX, got), SL(OY, got), SL(OZ, got));
+                d = f3(SL(DX, got), SL(DY, got), SL(DZ, got));  // unit length (the service round normalised it)
+                time = SL(TIME, got);
+                self_ref = SLI(SELF, got);
+                hit.t = SL(HT, got);  // the big list was tested when the ray was made: traversal starts with a finite tmax
+                hit.ref = SLI(HREF, got);
+                if (HAS_B) {
+                    hit.b1 = SL(HB1, got);
+                    hit.b2 = SL(HB2, got);
+                }
+                if (PRIMS & PRIMS_MEDIA) ray_rnd = (unsigned)SLI(RND, got);
+                inv_d = safe_inv(d);
+                oi = o * inv_d;
+                tmin = fmaf(1e-5f, max_abs(o), 1e-6f);  // ow_tmin with |d| = 1
+                if (PRIMS & PRIMS_TRIS) shear = make_shear(o, d);
+                st.sp = 0;
+                node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
+            }
+        }
+        const int n_act = __popc(__ballot_sync(FULL, slot >= 0));
+        // ================= (C) service: a full batch whenever one is waiting; a partial one when this warp runs dry =================
+        const int n_done = (int)(ctl.d_tail - ctl.d_head);
+        const int do_svc = __shfl_sync(FULL, (n_done >= 32 || (n_done > 0 && n_act <= svc_lo)) ? 1 : 0, 0);
+        if (do_svc) {
+            const int id = ring_pop(ring_d, &ctl.d_head, &ctl.d_tail, FULL, true, lane);
+            bool has_item = false, alive = false, requeue = false;
+            int s = 0, s_end = 0, xy = 0;
+            unsigned pixel = 0;
+            Path p;
+            p.depth = 0;
+            if (id >= 0) {
+                has_item = SLI(CHUNK, id) >= 0;
+                alive = (SLI(FLAGS, id) & 1) != 0;
+                if (has_item) {
+                    s = SLI(S, id);
+                    s_end = SLI(SEND, id);
+                    xy = SLI(XY, id);
+                    pixel = (unsigned)((xy >> 16) * cam.width + (xy & 0xffff));
+                }
+            }
+            if (MODE == MODE_TRACE) {
+                if (alive) {  // a traced ray came back: write its rl_hit (t in the caller's units: the ray ran with |d| = 1)
+                    rl_hit out;
+                    const int ref = SLI(HREF, id);
+                    out.node = -1;
+                    out.t = SL(HT, id) * SL(THRX, id);
+                    out.u = HAS_B ? SL(HB1, id) : 0.0f;
+                    out.v = HAS_B ? SL(HB2, id) : 0.0f;
+                    if (ref >= 0) {
+                        const int type = ref_type(ref), idx = ref_index(ref);
+                        out.node = type == REF_SPHERE ? sc.sphere_node[idx]
+                                 : type == REF_QUAD ? sc.quad_node[idx]
+                                 : type == REF_TRI ? __float_as_int(sc.tri_verts[idx].p1.w) : -1;
+                    }
+                    tio.hits[s] = out;
+                    alive = false;
+                    has_item = false;
+                }
+            } else {
+                if (alive) {  // its traversal finished: hit record + emitted + scatter
+                    p.o = f3(SL(OX, id), SL(OY, id), SL(OZ, id));
+                    p.d = f3(SL(DX, id), SL(DY, id), SL(DZ, id));
+                    p.time = SL(TIME, id);
+                    p.self_ref = SLI(SELF, id);
+                    p.thr = f3(SL(THRX, id), SL(THRY, id), SL(THRZ, id));
+                    p.depth = SLI(DEPTH, id);
+                    OwHit h;
+                    h.t = SL(HT, id);
+                    h.ref = SLI(HREF, id);
+                    h.b1 = HAS_B ? SL(HB1, id) : 0.0f;
+                    h.b2 = HAS_B ? SL(HB2, id) : 0.0f;
+                    const unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
+                    const uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
+                    float3 rad;
+                    if (!ow_shade<COUNT, PRIMS>(sc, cam, p, h, rnd, rad, lc)) {
+                        SL(ACCX, id) += rad.x;  // samples are folded in order (camera.rs:174)
+                        SL(ACCY, id) += rad.y;
+                        SL(ACCZ, id) += rad.z;
+                        alive = false;
+                        s++;
+                    }
+                }
+                if (has_item && !alive && s == s_end) {
+                    // ONE 16-byte store per finished item (over NVLink when the buffer is rank 0's)
+                    const size_t idx = ((size_t)SLI(CHUNK, id) * cam.height + (xy >> 16)) * cam.width + (xy & 0xffff);
+                    reinterpret_cast<float4*>(partial)[idx] = make_float4(SL(ACCX, id), SL(ACCY, id), SL(ACCZ, id), 0.0f);
+                    has_item = false;
+                    retired++;
+                }
+            }
+            // ---- slots without an item take one from the CTA's reserved batch ----
+            const bool need = id >= 0 && !has_item;
+            const unsigned m_need = __ballot_sync(FULL, need);
+            bool dead = false;
+            if (m_need) {
+                const int leader = __ffs(m_need) - 1;
+                long long start = 0;
+                int take = 0, dry = 0;
+                if ((int)lane == leader)
+                    take = items_take(ctl, __popc(m_need), n_items, queue, sys_queue, qbatch, q_guided, &start, &dry);
+                take = __shfl_sync(FULL, take, leader);
+                dry = __shfl_sync(FULL, dry, leader);
+                start = __shfl_sync(FULL, start, leader);
+                if (need) {
+                    const int rank_in = __popc(m_need & ((1u << lane) - 1u));
+                    if (rank_in < take) {
+                        const long long item = start + rank_in;
+                        if (MODE == MODE_TRACE) {
+                            const rl_ray r = tio.rays[item];
+                            p.o = f3(r.origin[0], r.origin[1], r.origin[2]);
+                            p.d = f3(r.direction[0], r.direction[1], r.direction[2]);
+                            p.time = r.time;
+                            p.self_ref = tio.self_refs ? tio.self_refs[item] : -1;
+                            p.thr = f3(rsqrtf(dot(p.d, p.d)), 0.0f, 0.0f);  // t(caller) = t(unit direction) / |d|
+                            p.depth = 1;
+                            s = (int)item;
+                            s_end = s + 1;
+                            SLI(CHUNK, id) = 0;
+                            SLI(SEND, id) = s_end;
+                            has_item = true;
+                            alive = true;
+                        } else {
+                            const int j = find_job(jt, item);
+                            const rl_job job = jt_job(jt, j);
+                            const long long local = item - jt_prefix(jt, j);
+                            const int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
+                            const long long pp = padded_pixels(w, hgt);
+                            const int ck = (int)(local / pp);
+                            int px, py;
+                            tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
+                            if (px < w && py < hgt) {
+                                const int x = job.x0 + px, y = job.y0 + py, chunk = job.chunk_begin + ck;
+                                ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                                if (cam.max_depth <= 0) s = s_end;  // depth 0: every sample is black (camera.rs:239-241)
+                                xy = (y << 16) | x;
+                                pixel = (unsigned)(y * cam.width + x);
+                                SLI(XY, id) = xy;
+                                SLI(SEND, id) = s_end;
+                                SLI(CHUNK, id) = chunk;
+                                SL(ACCX, id) = SL(ACCY, id) = SL(ACCZ, id) = 0.0f;
+                                has_item = true;
+                            } else {
+                                requeue = true;  // a padded slot outside the rectangle: try again next round
+                            }
+                        }
+                    } else if (dry) {
+                        dead = true;
+                    } else {
+                        requeue = true;  // the reserved batch ran out under this request: the next round installs a new one
+                    }
+                    if (!has_item) SLI(CHUNK, id) = -1;
+                }
+            }
+            if (MODE == MODE_RENDER && has_item && !alive && s < s_end) {  // path regeneration
+                ow_camera_ray(cam, xy & 0xffff, xy >> 16, (unsigned)(cam.first_sample + s), p);
+                alive = true;
+            }
+            // ---- new ray: unit direction, big list, slot write-back ----
+            if (alive) {
+                p.d = p.d * rsqrtf(dot(p.d, p.d));
+                const float tm = fmaf(1e-5f, max_abs(p.o), 1e-6f);
+                TriShear sh;
+                sh.k = 0; sh.Sx = sh.Sy = sh.Sz = 0.0f;
+                if (PRIMS & PRIMS_TRIS) sh = make_shear(p.o, p.d);
+                unsigned rr = 0u;
+                if ((PRIMS & PRIMS_MEDIA) && MODE == MODE_RENDER)
+                    rr = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
+                OwHit h0;
+                h0.t = RL_INF; h0.ref = -1; h0.b1 = h0.b2 = 0.0f;
+                if (COUNT) lc.rays++;
+                for (int k = 0; k < sc.n_big; k++)  // the big list: once per ray, here, with a full batch
+                    ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, sh, p.time, p.self_ref, tm, h0, lc, rr);
+                SL(OX, id) = p.o.x; SL(OY, id) = p.o.y; SL(OZ, id) = p.o.z;
+                SL(DX, id) = p.d.x; SL(DY, id) = p.d.y; SL(DZ, id) = p.d.z;
+                SL(TIME, id) = p.time;
+                SLI(SELF, id) = p.self_ref;
+                SL(THRX, id) = p.thr.x; SL(THRY, id) = p.thr.y; SL(THRZ, id) = p.thr.z;
+                SLI(DEPTH, id) = p.depth;
+                SL(HT, id) = h0.t;
+                SLI(HREF, id) = h0.ref;
+                if (HAS_B) {
+                    SL(HB1, id) = h0.b1;
+                    SL(HB2, id) = h0.b2;
+                }
+                if (PRIMS & PRIMS_MEDIA) SLI(RND, id) = (int)rr;
+            }
+            if (id >= 0 && !dead) {
+                SLI(S, id) = s;
+                SLI(FLAGS, id) = alive ? 1 : 0;
+                if (!alive) requeue = true;  // an item that is finished (or black) waits for the next round to retire
+            }
+            __threadfence_block();
+            ring_push(ring_r, &ctl.r_tail, __ballot_sync(FULL, alive), alive, id, lane);
+            ring_push(ring_d, &ctl.d_tail, __ballot_sync(FULL, requeue && !alive), requeue && !alive, id, lane);
+            const unsigned m_dead = __ballot_sync(FULL, dead);
+            if (m_dead && lane == 0) atomicSub((int*)&ctl.live, __popc(m_dead));
+            spins = 0;
+            continue;
+        }
+        if (n_act == 0) {  // nothing to traverse, nothing to service: done, or the other warps hold every live slot
+            if (__shfl_sync(FULL, (ctl.live <= 0 || ctl.abort) ? 1 : 0, 0)) break;  // lane 0 decides for the warp
+            __nanosleep(128);
+            if (++spins > (1u << 24)) {  // watchdog: report instead of hanging the GPU (~ 2 s of polling)
+                ctl.abort = 1;
+                lc.overflow++;
+                break;
+            }
+            continue;
+        }
+        spins = 0;
+        // ================= (D) traversal: node steps / leaf rounds until exit_min lanes have finished their rays =================
+        const int n_idle0 = 32 - n_act;
+        while (true) {
+            if (node < 0 && node != TRAV_END) {  // leaf round: every lane parked at a leaf tests it and pops
+                ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, o, d, shear, time, self_ref, tmin, hit, lc, ray_rnd);
+                node = st.pop();
+            }
+            const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));  // idle lanes count as ended
+            if (n_end == 32 || n_end - n_idle0 >= exit_min) break;
+            if (n_idle0 >= 4 && __shfl_sync(FULL, ctl.r_tail != ctl.r_head ? 1 : 0, 0)) break;  // rays appeared for the idle lanes
+            // node steps, until leaf_min lanes have parked (or ended) or none can step
+            const int keep = 32 - n_end - leaf_min;
+            int n_in;
+            do {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {  // two steps per ballot (measured in round 1: 1 / 2 / 3 / 4 -> 12.44 / 12.11 / 12.39 / 12.63 ms)
+                    if (node >= 0) bvh2_step<COUNT>(sc.nodes, node, st, inv_d, oi, tmin, hit.t, lc);
+                }
+                n_in = __popc(__ballot_sync(FULL, node >= 0));
+            } while (n_in > keep && n_in > 0);
+        }
+    }
+#undef SL
+#undef SLI
+    // completion accounting: items this GPU stored, added to the counter next to the queue (rank 0's over NVLink when the
+    // queue is shared), so the owner can tell a finished render from one a peer dropped out of
+    if (MODE == MODE_RENDER) {
+        for (int off = 16; off > 0; off >>= 1) retired += __shfl_xor_sync(FULL, retired, off);
+        if (lane == 0 && retired) {
+            if (sys_queue) atomicAdd_system(queue + 1, (unsigned long long)retired);
+            else atomicAdd(queue + 1, (unsigned long long)retired);
+        }
     }
     lc.flush(counters);
 }
@@ -855,44 +1153,15 @@ __global__ void k_encode_ow_u8(const float* __restrict__ sum, uint8_t* __restric
     out[i] = (uint8_t)(f != f ? 0.0 : fmin(fmax(f, 0.0), 255.0));
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_ow_trace(DevScene sc, const rl_ray* __restrict__ rays, unsigned long long n,
-                                                  rl_hit* __restrict__ hits, Counters* counters) {
-    LocalCount<COUNT> lc;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        rl_ray r = rays[i];
-        float3 o = f3(r.origin[0], r.origin[1], r.origin[2]), d = f3(r.direction[0], r.direction[1], r.direction[2]);
-        OwHit h = ow_closest<COUNT>(sc, o, d, r.time, -1, 1e-10f, lc);
-        rl_hit out;
-        out.node = -1;
-        out.t = h.t;
-        out.u = h.b1;
-        out.v = h.b2;
-        if (h.ref >= 0) {
-            int type = ref_type(h.ref), idx = ref_index(h.ref);
-            out.node = type == REF_SPHERE ? sc.sphere_node[idx]
-                     : type == REF_QUAD ? sc.quad_node[idx] : __float_as_int(sc.tri_verts[idx].p1.w);
-        }
-        hits[i] = out;
-    }
-    lc.flush(counters);
-}
-
 }  // namespace
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
 // Samples are cut into chunks of >= 8 (at most 64 chunks) plus the small tail chunks of ow_chunk_range (kernels.h): the
-// chunk is the unit of work a lane owns, so it bounds both the load-balancing tail (a 32-sample item was 1.7 ms of lane
-// time, 10 % of an 8-GPU cover-scene step) and the size of the partial-sum buffer (<= 64 frames).
+// chunk is the unit of work a path slot owns, so it bounds both the load-balancing tail (a 32-sample item was 1.7 ms of
+// lane time, 10 % of an 8-GPU cover-scene step) and the size of the partial-sum buffer (<= 64 frames).  A function of
+// spp ALONE: every rank of a multi-GPU render computes the same partition (round 1 read two environment variables here).
 int ow_num_chunks(int spp) {
     if (spp <= 0) return 1;
-    static const int min_chunk = env_int("RL_OW_CHUNK", 8);  // experiments only: every rank must agree
-    static const int max_chunks = env_int("RL_OW_MAXCHUNKS", 64);
+    constexpr int min_chunk = 8, max_chunks = 64;
     const int t = ow_tail_chunks(spp), body = spp - t * OW_TAIL_SIZE;
     int per_chunk = (body + (max_chunks - t) - 1) / (max_chunks - t);
     if (per_chunk < min_chunk) per_chunk = min_chunk;
@@ -954,75 +1223,115 @@ static OwCam make_cam(const rl_ow_camera* p, uint32_t first_sample) {
 }
 
 
-cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
-                             float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
-                             int sm_count, cudaStream_t stream, bool shared_queue) {
-    if (jt.n_items <= 0) return cudaSuccess;
-    OwCam c = make_cam(cam, first_sample);
-    cudaError_t e = cudaSuccess;
-    if (!shared_queue) e = cudaMemsetAsync(d_queue, 0, sizeof(unsigned long long), stream);  // the owner resets a shared queue
-    if (e != cudaSuccess) return e;
-    const int sysq = shared_queue ? 1 : 0;
-    // Kernel variants stay selectable for A/B profiling (DESIGN.md §"OW kernel variants", profiles/r01_ncu_k_ow_render_*):
-    //   RL_OW_KERNEL_V=3  while-while traversal, FMA slabs, cull-free pop; a bounce ends with the warp's slowest lane
-    //   RL_OW_KERNEL_V=5  resumable traversal + threshold-triggered service, one node step per iteration with batched
-    //                     leaf tests (default); RL_OW_LEAF=32 degenerates to while-while inner loops ("v4")
-    //   RL_OW_MINB = resident CTAs per SM the kernel is compiled for (register budget), RL_OW_SVC = lanes that must
-    //   wait before the warp leaves the traversal loop to service them, RL_OW_LEAF = parked lanes per leaf round.
-    // (v1, the per-lane if-if loop, and v2, the one-action-per-step state machine, lost to v3 and were removed; their
-    //  ncu summaries stay under profiles/.)
-    static const int variant = env_int("RL_OW_KERNEL_V", 5);
-    static const int minb_env = env_int("RL_OW_MINB", 0);
-    static const int svc_env = env_int("RL_OW_SVC", 0), leaf_env = env_int("RL_OW_LEAF", 0);
-    static const int generic = env_int("RL_OW_GENERIC", 0);
-    static const int opt = env_int("RL_OW_OPT", 0);  // experiments: node steps per ballot (2, 3, 4)  // 1: never pick the spheres-only instantiation
-    typedef void (*K3)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int);
-    typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
-    K3 k3 = nullptr;
-    K5 k4 = nullptr;
-    const bool extras = sc.n_media > 0 || sc.n_perlins > 0;  // constant media / Noise textures: the FULL build
-    const bool spheres_only = !generic && !extras && sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0;
-    const bool no_spheres = !generic && !extras && sc.n_spheres == 0;
-    // measured (profiles/r01_sweep_ow_v5.log and the C5 runs after it): the spheres-only and the no-spheres builds fit
-    // 64 registers (4 CTAs/SM) with 18 / 86 B of spills and win there (C5 @64 spp: 66.7 vs 69.4 ms); the build that
-    // carries every primitive kind is better at 80 registers (3 CTAs/SM)
-    const int minb = minb_env ? minb_env : ((spheres_only || no_spheres) ? 4 : 3);
-    // service threshold (profiles/r01_sweep_ow_v5b.log): sphere scenes shade cheaply and prefer fuller service rounds
-    // (C4: 12.50 ms at 24 vs 13.25 at 16); with triangles in the leaf rounds 16 is best (C5: 67.0 vs 74.0 at 24)
-    const int svc_min = svc_env ? svc_env : (spheres_only ? 24 : 16);
-    // parked lanes per leaf round, with two node steps per ballot: C4 11.9 ms at 6-10 vs 12.2 at 12; C5 64.7 at 10-12 vs 65.5 at 8
-    const int leaf_min = leaf_env ? leaf_env : (spheres_only ? 8 : 12);
-    constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
-    if (variant == 3 && !extras) {  // v3 predates media / Noise
-        k3 = instrumented ? (K3)k_ow_render<true, 1, 4> : (K3)k_ow_render<false, 1, 4>;
-    } else if (extras) {
-        k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FULL> : (K5)k_ow_render5<false, 3, PRIMS_FULL>;
-    } else if (spheres_only) {
-        if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_SPHERES> : (K5)k_ow_render5<false, 4, PRIMS_SPHERES>;
-        else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_SPHERES> : (K5)k_ow_render5<false, 3, PRIMS_SPHERES>;
-    } else if (no_spheres) {
-        if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_FLAT> : (K5)k_ow_render5<false, 4, PRIMS_FLAT>;
-        else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FLAT> : (K5)k_ow_render5<false, 3, PRIMS_FLAT>;
-    } else {
-        if (minb >= 4) k4 = instrumented ? (K5)k_ow_render5<true, 4, PRIMS_ALL> : (K5)k_ow_render5<false, 4, PRIMS_ALL>;
-        else k4 = instrumented ? (K5)k_ow_render5<true, 3, PRIMS_ALL> : (K5)k_ow_render5<false, 3, PRIMS_ALL>;
+namespace {
+constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
+typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
+typedef void (*K6)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int, int, int,
+                   v6::TraceIO);
+
+// which instantiation a scene runs: spheres only / no spheres / every surface / everything (media, Noise)
+int scene_prims(const DevScene& sc) {
+    if (sc.n_media > 0 || sc.n_perlins > 0) return PRIMS_FULL;
+    if (sc.n_tris == 0 && sc.n_quads == 0 && sc.n_images == 0) return PRIMS_SPHERES;
+    if (sc.n_spheres == 0) return PRIMS_FLAT;
+    return PRIMS_ALL;
+}
+
+template <int MODE>
+K6 pick_k6(int prims, int minb, bool instrumented) {
+#define RL_K6(P_)                                                                                                   \
+    (minb >= 4 ? (instrumented ? (K6)k_ow_render6<true, 4, P_, MODE> : (K6)k_ow_render6<false, 4, P_, MODE>)       \
+               : (instrumented ? (K6)k_ow_render6<true, 3, P_, MODE> : (K6)k_ow_render6<false, 3, P_, MODE>))
+    switch (prims) {
+        case PRIMS_SPHERES: return RL_K6(PRIMS_SPHERES);
+        case PRIMS_FLAT: return RL_K6(PRIMS_FLAT);
+        case PRIMS_ALL: return RL_K6(PRIMS_ALL);
+        default: return instrumented ? (K6)k_ow_render6<true, 3, PRIMS_FULL, MODE> : (K6)k_ow_render6<false, 3, PRIMS_FULL, MODE>;
     }
+#undef RL_K6
+}
+
+K5 pick_k5(int prims, int minb, bool instrumented) {
+#define RL_K5(P_)                                                                                       \
+    (minb >= 4 ? (instrumented ? (K5)k_ow_render5<true, 4, P_> : (K5)k_ow_render5<false, 4, P_>)       \
+               : (instrumented ? (K5)k_ow_render5<true, 3, P_> : (K5)k_ow_render5<false, 3, P_>))
+    switch (prims) {
+        case PRIMS_SPHERES: return RL_K5(PRIMS_SPHERES);
+        case PRIMS_FLAT: return RL_K5(PRIMS_FLAT);
+        case PRIMS_ALL: return RL_K5(PRIMS_ALL);
+        default: return instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FULL> : (K5)k_ow_render5<false, 3, PRIMS_FULL>;
+    }
+#undef RL_K5
+}
+
+// one v6 launch (render or trace): shared-memory size, occupancy, grid, batch sizes
+cudaError_t launch_k6(K6 k, int prims, const DevScene& sc, const OwCam& c, const JobTable& jt, float* d_partial,
+                      unsigned long long* d_queue, Counters* d_counters, int sm_count, cudaStream_t stream, bool shared_queue,
+                      const OwTuning& tune, const v6::TraceIO& tio) {
+    int P = tune.slots > 0 ? tune.slots : 384;
+    P = (P + 31) / 32 * 32;
+    if (P < 256) P = 256;  // at least one slot per lane, or lanes starve by construction
+    if (P > v6::QCAP) P = v6::QCAP;
+    const size_t smem = v6::smem_bytes(prims, P);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = k3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3, 256, 0)
-           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4, 256, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
     long long want = (jt.n_items + 255) / 256;
     long long grid = (long long)sm_count * per_sm;  // persistent: every SM full, a multiple of the SM count
     if (grid > want && !shared_queue) grid = want;
     if (grid < 1) grid = 1;
-    // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
+    // items a CTA reserves per global atomic: plenty while there is plenty of work, never so many that CTAs starve
+    long long per_cta = jt.n_items / (grid * 8);
+    const int qbatch = (int)(per_cta < 32 ? 32 : (per_cta > 256 ? 256 : per_cta));
+    // below this many remaining items a CTA reserves 32 instead of qbatch (a shared queue feeds up to 8 GPUs)
+    const long long q_guided = grid * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
+    const int svc_lo = tune.svc_lo > 0 ? tune.svc_lo : 16;
+    const int exit_min = tune.exit_min > 0 ? tune.exit_min : 8;
+    const int leaf_min = tune.leaf_min > 0 ? tune.leaf_min : (prims == PRIMS_SPHERES ? 8 : 12);
+    k<<<(unsigned)grid, 256, smem, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, shared_queue ? 1 : 0, qbatch, q_guided, P,
+                                             svc_lo, exit_min, leaf_min, tio);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
+                             float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
+                             int sm_count, cudaStream_t stream, bool shared_queue, const OwTuning& tune) {
+    if (jt.n_items <= 0) return cudaSuccess;
+    OwCam c = make_cam(cam, first_sample);
+    cudaError_t e = cudaSuccess;
+    if (!shared_queue) e = cudaMemsetAsync(d_queue, 0, 2 * sizeof(unsigned long long), stream);  // the owner resets a shared queue
+    if (e != cudaSuccess) return e;
+    const int prims = scene_prims(sc);
+    // resident CTAs per SM the kernel is compiled for (register budget): the spheres-only and no-spheres builds fit 64
+    // registers (4 CTAs/SM); the builds that carry every primitive kind are better at 80 (3 CTAs/SM)
+    const int minb = tune.minb ? tune.minb : ((prims == PRIMS_SPHERES || prims == PRIMS_FLAT) ? 4 : 3);
+    if (tune.variant != 5) {
+        v6::TraceIO tio{nullptr, nullptr, nullptr};
+        return launch_k6(pick_k6<v6::MODE_RENDER>(prims, minb, instrumented), prims, sc, c, jt, d_partial, d_queue, d_counters,
+                         sm_count, stream, shared_queue, tune, tio);
+    }
+    // v5 (round 1's kernel: per-lane paths, threshold-triggered service inside the warp), kept as the measured A/B baseline
+    K5 k5 = pick_k5(prims, minb, instrumented);
+    const int svc_min = tune.svc_min > 0 ? tune.svc_min : (prims == PRIMS_SPHERES ? 24 : 16);
+    const int leaf_min = tune.leaf_min > 0 ? tune.leaf_min : (prims == PRIMS_SPHERES ? 8 : 12);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (jt.n_items + 255) / 256;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > want && !shared_queue) grid = want;
+    if (grid < 1) grid = 1;
     long long per_warp = jt.n_items / (grid * 8 * 4);
     int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
-    // below this many remaining items a warp reserves 32 instead of qbatch (a shared queue feeds up to 8 GPUs)
     const long long q_guided = grid * 8 * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
-    if (k3) k3<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch);
-    else k4<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, sysq, qbatch, q_guided, svc_min, leaf_min);
+    k5<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, shared_queue ? 1 : 0, qbatch, q_guided, svc_min,
+                                           leaf_min);
     return cudaGetLastError();
 }
 
@@ -1045,13 +1354,25 @@ cudaError_t launch_encode_ow_u8(const float* d_rgb_sum, uint8_t* d_out, size_t n
     return cudaGetLastError();
 }
 
-cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t n, rl_hit* d_hits, Counters* d_counters,
-                            bool instrumented, cudaStream_t stream) {
+// rl_trace_batch for OW scenes: the rays run through the render kernel's own queues, big-list start, node steps and leaf
+// rounds (k_ow_render6 in MODE_TRACE).  d_self_refs (optional) = the leaf ref each ray starts on.
+cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, const int* d_self_refs, uint64_t n, rl_hit* d_hits,
+                            unsigned long long* d_queue, Counters* d_counters, bool instrumented, int sm_count,
+                            cudaStream_t stream, const OwTuning& tune) {
     if (n == 0) return cudaSuccess;
-    unsigned blocks = (unsigned)((n + 127) / 128);
-    if (instrumented) k_ow_trace<true><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
-    else k_ow_trace<false><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_counters);
-    return cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(d_queue, 0, 2 * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    OwCam c{};
+    c.width = 1;
+    c.max_depth = 1;
+    JobTable jt{};
+    jt.inline_jobs = 1;
+    jt.n_items = (long long)n;
+    const int prims = scene_prims(sc);
+    const int minb = tune.minb ? tune.minb : ((prims == PRIMS_SPHERES || prims == PRIMS_FLAT) ? 4 : 3);
+    v6::TraceIO tio{d_rays, d_self_refs, d_hits};
+    return launch_k6(pick_k6<v6::MODE_TRACE>(prims, minb, instrumented), prims, sc, c, jt, nullptr, d_queue, d_counters, sm_count,
+                     stream, false, tune, tio);
 }
 
 }  // namespace rl

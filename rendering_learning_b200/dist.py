@@ -113,54 +113,79 @@ def render_ow_distributed(ctx, cam, first_sample: int, jobs: Sequence[Job], part
 
 
 def setup_shared_queue(ctx, partial_bytes: int = 0) -> bool:
-    """Map rank 0's work counter (and, with partial_bytes > 0, its partial-sum buffer) into every rank with
-    CUDA IPC.  Returns False when there is a single rank."""
+    """Map rank 0's control block (and, with partial_bytes > 0, its RL_QUEUE_SLOTS partial-sum buffers of that size)
+    into every rank with CUDA IPC.  The size travels WITH the handle, so a rank cannot launch a camera that does not
+    fit the owner's buffer.  Returns False when there is a single rank."""
     import torch.distributed as dist
     rank, world = _rank_world()
     if world == 1:
         return False
-    box = [None, None]
+    box = [None, None, 0]
     if rank == 0:
-        box = [ctx.queue_export(), ctx.partial_export(partial_bytes) if partial_bytes else None]
+        box = [ctx.queue_export(), ctx.partial_export(partial_bytes) if partial_bytes else None, int(partial_bytes)]
+        ctx.queue_reset(0, 0)  # slot 0 is ready for the first render; every render resets the OTHER slot for the next one
+        ctx.synchronize()
     dist.broadcast_object_list(box, src=0)
     if rank != 0:
         ctx.queue_import(box[0])
         if box[1] is not None:
-            ctx.partial_import(box[1])
+            ctx.partial_import(box[1], box[2])
     dist.barrier()
+    _fused_state["render"] = 0
     return True
 
 
+_fused_state = {"render": 0}
+
+
 def render_ow_fused(ctx, cam, first_sample: int, out, n_chunks: int, height: int, width: int):
-    """OW render, fully device-driven: every GPU's persistent warps pop items from rank 0's counter and store
-    the finished partial sums straight into rank 0's buffer, both over NVLink peer memory.  The only
-    collectives are two 4-byte NCCL all-reduces used as stream-ordered rendezvous."""
+    """OW render, fully device-driven: every GPU's persistent warps pop items from rank 0's counter and store the
+    finished partial sums straight into rank 0's buffer, both over NVLink peer memory.
+
+    Renders alternate between two {counter, partial buffer} slots.  Rank 0 resets the slot of render i + 1 on its stream
+    BEFORE its own kernel of render i, i.e. before it joins render i's closing rendezvous — which every rank must pass
+    before it launches render i + 1.  So a rank launches without waiting for anybody (a rank whose host thread is late
+    simply pops fewer items) and the only collective is ONE 4-byte NCCL all-reduce at the end of the render, after
+    which rank 0 checks the completion counter and folds."""
     import torch.distributed as dist
     rank, world = _rank_world()
     stream = current_stream_handle()
-    tok = _token(out.device)
+    slot = _fused_state["render"] & 1
+    _fused_state["render"] += 1
+    jobs = [(0, 0, width, height, 0, n_chunks)]
     if rank == 0:
-        ctx.queue_reset(stream)
-    dist.all_reduce(tok)  # no rank pops before the reset
-    ctx.render_ow_shared(cam, first_sample, [(0, 0, width, height, 0, n_chunks)], 0, stream)
-    dist.all_reduce(tok)  # every rank's stores have landed
+        ctx.queue_reset(stream, slot ^ 1)
+    ctx.render_ow_shared(cam, first_sample, jobs, 0, stream, slot)
+    dist.all_reduce(_token(out.device))  # every rank's kernel has finished: its stores have landed in rank 0's HBM
     if rank == 0:
-        ctx.ow_reduce_device(cam, 0, out.data_ptr(), stream)
+        ctx.ow_reduce_shared(cam, slot, out.data_ptr(), stream)
+        return slot
+    return None
+
+
+def check_fused_complete(ctx, cam, slot: int, n_chunks: int, height: int, width: int):
+    """rank 0, after render_ow_fused: the completion counter must equal the number of work items — a rank that died
+    (or a kernel that aborted) leaves it short instead of leaving silent zeros in the frame.  Synchronises the stream."""
+    want = ctx.ow_job_items(cam, [(0, 0, width, height, 0, n_chunks)])
+    got = ctx.queue_completed(current_stream_handle(), slot)
+    if got != want:
+        raise RuntimeError(f"multi-GPU render incomplete: {got} of {want} work items were stored")
 
 
 def render_ow_shared_queue(ctx, cam, first_sample: int, partial, out, n_chunks: int, height: int, width: int):
     """OW render with the cross-GPU device queue: one persistent launch per GPU, warps of every GPU pop
-    (pixel x sample-chunk) items from rank 0's counter over NVLink; NCCL sum-gathers the partial sums."""
+    (pixel x sample-chunk) items from rank 0's counter over NVLink; NCCL sum-gathers the partial sums (the comparison
+    point for the fused gather above)."""
     import torch
     import torch.distributed as dist
     rank, world = _rank_world()
     stream = current_stream_handle()
+    slot = _fused_state["render"] & 1
+    _fused_state["render"] += 1
     partial.zero_()
     if rank == 0:
-        ctx.queue_reset(stream)
-    # stream-ordered rendezvous: no rank pops before the owner's reset has executed
-    dist.all_reduce(_token(partial.device))
-    ctx.render_ow_shared(cam, first_sample, [(0, 0, width, height, 0, n_chunks)], partial.data_ptr(), stream)
+        ctx.queue_reset(stream, slot ^ 1)
+    ctx.render_ow_shared(cam, first_sample, [(0, 0, width, height, 0, n_chunks)], partial.data_ptr(), stream, slot)
     dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM)
     if rank == 0:
         ctx.ow_reduce_device(cam, partial.data_ptr(), out.data_ptr(), stream)

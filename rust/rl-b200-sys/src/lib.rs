@@ -5,7 +5,8 @@
 
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RL_B200_ABI_VERSION: i32 = 2;
+pub const RL_B200_ABI_VERSION: i32 = 3;
+pub const RL_QUEUE_SLOTS: i32 = 2;
 
 pub const RL_OK: c_int = 0;
 pub const RL_E_INVALID: c_int = -1;
@@ -256,6 +257,8 @@ pub struct rl_ctx {
 
 extern "C" {
     pub fn rl_create(device_id: c_int, out: *mut *mut rl_ctx) -> c_int;
+    pub fn rl_create_multi(device_ids: *const i32, n: i32, out: *mut *mut rl_ctx) -> c_int;
+    pub fn rl_device_count(ctx: *const rl_ctx) -> c_int;
     pub fn rl_destroy(ctx: *mut rl_ctx);
     pub fn rl_last_error(ctx: *const rl_ctx) -> *const c_char;
     pub fn rl_abi_version() -> c_int;
@@ -270,6 +273,7 @@ extern "C" {
     pub fn rl_lbvh_download(ctx: *mut rl_ctx, out: *mut rl_lbvh_host) -> c_int;
 
     pub fn rl_trace_batch(ctx: *mut rl_ctx, rays: *const rl_ray, n: u64, out: *mut rl_hit) -> c_int;
+    pub fn rl_trace_batch_ex(ctx: *mut rl_ctx, rays: *const rl_ray, self_nodes: *const i32, n: u64, out: *mut rl_hit) -> c_int;
 
     pub fn rl_render_rtc(ctx: *mut rl_ctx, cam: *const rl_rtc_camera, anti_aliasing_samples: u32, out_rgb: *mut f32,
                          stats: *mut rl_stats) -> c_int;
@@ -292,11 +296,16 @@ extern "C" {
 
     pub fn rl_queue_export(ctx: *mut rl_ctx, handle64: *mut c_void) -> c_int;
     pub fn rl_queue_import(ctx: *mut rl_ctx, handle64: *const c_void) -> c_int;
-    pub fn rl_queue_reset(ctx: *mut rl_ctx, stream: *mut c_void) -> c_int;
-    pub fn rl_partial_export(ctx: *mut rl_ctx, bytes: u64, handle64: *mut c_void) -> c_int;
-    pub fn rl_partial_import(ctx: *mut rl_ctx, handle64: *const c_void) -> c_int;
+    pub fn rl_queue_reset(ctx: *mut rl_ctx, stream: *mut c_void, slot: i32) -> c_int;
+    pub fn rl_queue_completed(ctx: *mut rl_ctx, stream: *mut c_void, slot: i32, items: *mut u64) -> c_int;
+    pub fn rl_partial_export(ctx: *mut rl_ctx, bytes_per_slot: u64, n_slots: i32, handle64: *mut c_void) -> c_int;
+    pub fn rl_partial_import(ctx: *mut rl_ctx, handle64: *const c_void, bytes_per_slot: u64, n_slots: i32) -> c_int;
     pub fn rl_render_ow_shared(ctx: *mut rl_ctx, cam: *const rl_ow_camera, first_sample: u32, jobs: *const rl_job,
-                               n_jobs: i32, d_partial: *mut c_void, stream: *mut c_void) -> c_int;
+                               n_jobs: i32, d_partial: *mut c_void, stream: *mut c_void, slot: i32) -> c_int;
+    pub fn rl_ow_reduce_shared(ctx: *mut rl_ctx, cam: *const rl_ow_camera, slot: i32, d_out_rgb_sum: *mut c_void,
+                               stream: *mut c_void) -> c_int;
+    pub fn rl_ow_job_items(cam: *const rl_ow_camera, jobs: *const rl_job, n_jobs: i32) -> i64;
+    pub fn rl_set_option(ctx: *mut rl_ctx, name: *const c_char, value: i32) -> c_int;
 
     pub fn rl_set_instrumented(ctx: *mut rl_ctx, enabled: c_int) -> c_int;
 }

@@ -46,6 +46,22 @@ impl Ctx {
         Ok(Ctx { raw })
     }
 
+    /// One context over several GPUs of one node (`rl_create_multi`): `render_ow` / `render_rtc` then use all of them
+    /// — dynamic (pixel x sample-chunk) queue in GPU 0's HBM, partial sums stored over NVLink, bit-identical image.
+    pub fn new_multi(device_ids: &[i32]) -> Result<Self> {
+        let mut raw = ptr::null_mut();
+        let rc = unsafe { sys::rl_create_multi(device_ids.as_ptr(), device_ids.len() as i32, &mut raw) };
+        if rc != sys::RL_OK {
+            return Err(Self::error_of(ptr::null(), rc));
+        }
+        assert_eq!(unsafe { sys::rl_abi_version() }, sys::RL_B200_ABI_VERSION);
+        Ok(Ctx { raw })
+    }
+
+    pub fn device_count(&self) -> i32 {
+        unsafe { sys::rl_device_count(self.raw) }
+    }
+
     fn error_of(raw: *const sys::rl_ctx, rc: i32) -> Error {
         let msg = unsafe { CStr::from_ptr(sys::rl_last_error(raw)) }.to_string_lossy().into_owned();
         match rc {
