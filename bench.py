@@ -2,24 +2,27 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload C4|C5|C1|C2|C3] [--impl reference]
 
-A "step" is one complete render of the workload.  Default workload = BASELINE.json's headline: the RTIOW
-cover scene at 1200x675, 500 spp, depth 50 (config C4); the teapot (C3, 3840x2160) is measured beside it at
-N = 1 and reported under "secondary".  For N > 1 the driver launches this file under torchrun (one rank per
-GPU); the image is cut into tile x sample-chunk jobs pulled from a dynamic queue and the framebuffer is
-gathered to rank 0 with NCCL.  Rank 0 prints ONE JSON line.
+A "step" is one complete render of the workload.  Default workload = BASELINE.json's headline: the RTIOW cover scene
+at 1200x675, 500 spp, depth 50 (config C4).  Beside it, under "secondary": the textured spot mesh (C5, 3840x2160, 256
+spp) at every N and the teapot (C3, 3840x2160) at N = 1.  For N > 1 the driver launches this file under torchrun (one
+rank per GPU): every GPU's persistent warps pop (pixel x sample-chunk) items from ONE counter in rank 0's HBM over
+NVLink and store finished items straight into rank 0's partial-sum buffer; rank 0 folds.  Rank 0 prints ONE JSON line.
 
-  value      whole-job Mrays/s with the scene resident in HBM, device-timed (CUDA events on the launching
-             stream), max over ranks.  rays = every ray cast (camera + secondary + shadow), counted by device
+  value      whole-job Mrays/s with the scene resident in HBM, device-timed: CUDA events around EXACTLY K back-to-back
+             steps (barrier + synchronize on both sides), max over ranks.  rays = every ray cast, counted by device
              atomics in a separate instrumented pass with the same seed.
-  e2e        the same metric through the public API (`Camera.render`): lowering, H2D scene upload, LBVH build,
-             render, D2H of the framebuffer into pinned host memory, every step.
-  roofline   algorithmic FP32 flops (SURVEY.md §8d constants x device counters) / kernel time vs the FP32
-             peak measured live on this GPU; L2 and HBM fractions beside it.  bound = "fp32": no stage of this
-             path is a dense contraction and the working set is L1/L2 resident.  `traffic` =
-             dram__bytes_read + dram__bytes_write of the same kernel at the same config from the committed
-             `ncu --set full` capture (profiles/ncu_<workload>.json, written by tools/ncu_traffic.py).
-  cpu_baseline  the oracle (a C++ f64 restatement of the reference; the Rust reference cannot be built in
-             this image) on all host cores, on a bounded sample of the same workload.
+  e2e        the same metric through the public API — the literal `Camera.render(world)` call (scenes.py worlds, the
+             reference's own types): lower the object tree, rl_scene_upload (flatten, H2D, LBVH build), render, D2H of
+             the framebuffer into PAGEABLE host memory, f64 Canvas — every step.  `e2e.prepared` is the same call given
+             an already-lowered scene (`Camera.render(scene_desc)`, the caller keeps the lowering).
+  roofline   what bounds the kernel is instruction issue x SIMT lane utilisation (bound = "issue"), not HBM and not
+             tensor cores (no stage is a dense contraction, the working set is L1 / L2 resident): `achieved` / `peak` /
+             `frac` are algorithmic FP32 flops (SURVEY.md §8d constants x device counters) / kernel time against the
+             FP32 FMA peak measured live on this GPU; `ncu` carries issue-slot utilisation, LSU wavefronts, lanes per
+             instruction and DRAM traffic of the same kernel from the committed `ncu --set full` capture
+             (profiles/ncu_<workload>.json, written by tools/ncu_summary.py), with the kernel signature it was taken on.
+  cpu_baseline  the oracle (a C++ f64 restatement of the reference; the Rust reference cannot be built in this image) on
+             all host cores (threads set explicitly — torchrun exports OMP_NUM_THREADS=1), on a bounded sample.
 """
 from __future__ import annotations
 
@@ -38,11 +41,11 @@ import numpy as np  # noqa: E402
 
 # algorithmic work per unit (definitions, fixed so numbers compare across commits)
 FLOPS = {"node": 28, "sphere": 36, "tri": 45, "quad": 40, "rtc_prim": 50, "rtc_shade": 110, "ow_scatter": 45, "camera": 40}
-BYTES_L2 = {"node": 64, "sphere": 32, "tri": 48, "quad": 64, "rtc_prim": 64, "rtc_shade": 48, "ow_scatter": 36}
+BYTES_L1 = {"node": 64, "sphere": 32, "tri": 48, "quad": 64, "rtc_prim": 64, "rtc_shade": 48, "ow_scatter": 36}
 
 
 def workloads():
-    from rendering_learning_b200 import ow, scenes
+    from rendering_learning_b200 import scenes
     return {
         "C4": dict(kind="ow", name="RTIOW cover scene (bouncing_spheres), 1200x675, 500 spp, depth 50",
                    world=scenes.ow_cover_world, params=lambda: scenes.ow_cover_params()),
@@ -57,18 +60,23 @@ def workloads():
     }
 
 
+def metric_name(wl: dict) -> str:
+    """ONE string for both arms (the driver refuses to divide lines whose metrics differ)."""
+    return f"Mrays/s, {wl['name']}"
+
+
 # ---- clocks -------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index: int, period_ms: int = 50):
+        self.rows, self.proc, self.idx, self.period = [], None, gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", str(self.period), "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -88,27 +96,32 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [r for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        # "under load" = samples drawing real power; idle samples between phases would drag the median down
+        pw = [float(r[3]) if r[3].replace(".", "").isdigit() else 0.0 for r in ok]
+        load = [r for r, p in zip(ok, pw) if p >= 0.5 * max(pw)] if pw else ok
+        sm = [float(r[1]) for r in (load or ok)]
+        mx = [float(r[2]) for r in ok if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in ok for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(ok), "samples_under_load": len(load),
+                "power_w_max": max(pw) if pw else None}
 
 
 # ---- helpers --------------------------------------------------------------------------------------------------
 def algorithmic(kind: str, st: dict, samples: int) -> tuple[float, float]:
-    """(flops, L2-level bytes) of one step from the instrumented counters."""
+    """(flops, L1-level bytes) of one step from the instrumented counters."""
     if kind == "ow":
         fl = (st["node_visits"] * FLOPS["node"] + st["prim_tests"] * FLOPS["sphere"] + st["tri_tests"] * FLOPS["tri"] +
               st["shades"] * FLOPS["ow_scatter"] + samples * FLOPS["camera"])
-        by = (st["node_visits"] * BYTES_L2["node"] + st["prim_tests"] * BYTES_L2["sphere"] +
-              st["tri_tests"] * BYTES_L2["tri"] + st["shades"] * BYTES_L2["ow_scatter"])
+        by = (st["node_visits"] * BYTES_L1["node"] + st["prim_tests"] * BYTES_L1["sphere"] +
+              st["tri_tests"] * BYTES_L1["tri"] + st["shades"] * BYTES_L1["ow_scatter"])
     else:
         fl = (st["node_visits"] * FLOPS["node"] + st["prim_tests"] * FLOPS["rtc_prim"] + st["tri_tests"] * FLOPS["tri"] +
               st["shades"] * FLOPS["rtc_shade"] + samples * FLOPS["camera"])
-        by = (st["node_visits"] * BYTES_L2["node"] + st["prim_tests"] * BYTES_L2["rtc_prim"] +
-              st["tri_tests"] * BYTES_L2["tri"] + st["shades"] * BYTES_L2["rtc_shade"])
+        by = (st["node_visits"] * BYTES_L1["node"] + st["prim_tests"] * BYTES_L1["rtc_prim"] +
+              st["tri_tests"] * BYTES_L1["tri"] + st["shades"] * BYTES_L1["rtc_shade"])
     return float(fl), float(by)
 
 
@@ -119,9 +132,20 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def ncu_summary(workload: str) -> dict:
+    pj = os.path.join(ROOT, "profiles", f"ncu_{workload}.json")
+    if os.path.exists(pj):
+        try:
+            return json.load(open(pj))
+        except Exception:
+            pass
+    return {}
+
+
 # ---- reference arm / cpu baseline: the oracle on the host cores ---------------------------------------------
-def cpu_run(wl: dict, budget_s: float):
-    """Time the CPU restatement on a bounded sample; returns (Mrays/s, samples/s, description, seconds)."""
+def cpu_run(wl: dict, budget_s: float, threads: int):
+    """Time the CPU restatement on a bounded sample; returns (Mrays/s, samples/s, description, seconds).  `threads` is
+    passed to OpenMP explicitly: under torchrun OMP_NUM_THREADS is 1 and omp_get_max_threads() would obey it."""
     from oracle import oracle as orc
     from rendering_learning_b200 import ow
     if wl["kind"] == "ow":
@@ -130,13 +154,13 @@ def cpu_run(wl: dict, budget_s: float):
         full_spp = params.samples_per_pixel
         params.samples_per_pixel = 1
         t0 = time.perf_counter()
-        orc.ow_render(desc, params.abi())
+        orc.ow_render(desc, params.abi(), threads=threads)
         t1 = time.perf_counter() - t0
         spp = int(max(2, min(full_spp, budget_s / max(t1, 1e-3))))
         params.samples_per_pixel = spp
         cam = params.abi()
         t0 = time.perf_counter()
-        sums, rays = orc.ow_render(desc, cam)
+        sums, rays = orc.ow_render(desc, cam, threads=threads)
         dt = time.perf_counter() - t0
         samples = sums.shape[0] * sums.shape[1] * spp
         what = (f"full {sums.shape[1]}x{sums.shape[0]} frame at {spp} spp of {full_spp} "
@@ -144,22 +168,17 @@ def cpu_run(wl: dict, budget_s: float):
         return rays / dt / 1e6, samples / dt, what, dt
     sc = wl["scene"]()
     desc = sc.world.lower()
-    cam = sc.camera.abi()
-    rows = cam.vsize
-    full = (cam.hsize, cam.vsize)
-    # bounded: shrink the frame (same scene, same aspect) until one render fits the budget
+    full = (sc.camera.abi().hsize, sc.camera.abi().vsize)
     from rendering_learning_b200 import rtc
     scale = 1
-    while True:
+    while True:  # bounded: shrink the frame (same scene, same aspect) until one render fits the budget
         c2 = rtc.Camera.new(full[0] // scale, full[1] // scale, sc.camera.fov, sc.camera.transform).abi()
         t0 = time.perf_counter()
-        orc.rtc_render(desc, c2, 1)
+        orc.rtc_render(desc, c2, 1, threads=threads)
         dt = time.perf_counter() - t0
         if dt <= budget_s or scale >= 8:
             break
         scale *= 2
-    rays = orc.rtc_camera_rays(c2, 1)
-    # rays per pixel of the oracle = the GPU's instrumented count per pixel (same algorithm); report pixels/s too
     what = f"{c2.hsize}x{c2.vsize} frame (1/{scale} linear size of {full[0]}x{full[1]}), 1 spp"
     return None, c2.hsize * c2.vsize / dt, what, dt
 
@@ -171,35 +190,152 @@ def reference_arm(args, wl_key: str):
     wl = workloads()[wl_key]
     from oracle import oracle as orc
     orc.build()
+    cores = host_cores()
     per_step = args.cpu_seconds or (8.0 if wl["kind"] == "ow" else 20.0)
     vals, what, secs, sps = [], "", [], []
     for i in range(args.warmup + args.steps):
-        v, s, what, dt = cpu_run(wl, per_step)
+        v, s, what, dt = cpu_run(wl, per_step, cores)
         if i >= args.warmup:
             vals.append(v)
             secs.append(dt)
             sps.append(s)
         if i == 0 and dt * (args.warmup + args.steps) > 240:
             per_step = max(1.0, per_step / 2)
-    cores = host_cores()
-    if vals[0] is None:  # RTC: express as Mrays/s with the GPU-countable rays/pixel unavailable -> use primary rays
-        value = float(np.mean(sps)) / 1e6
-        unit = "Mpixels/s"
+    if vals[0] is None:  # RTC: the oracle does not count rays; report pixels
+        value, unit = float(np.mean(sps)) / 1e6, "Mpixels/s"
     else:
         value, unit = float(np.mean(vals)), "Mrays/s"
-    line = {"metric": f"Mrays/s, {wl['name']}", "impl": "reference", "value": value, "unit": unit,
+    line = {"metric": metric_name(wl), "impl": "reference", "value": value, "unit": unit,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": what},
             "samples_per_s": float(np.mean(sps)),
-            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": what},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "threads": cores, "kind": "port", "sample": what,
+                             "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement (C++ f64, OpenMP over rows/columns like the reference's rayon loop) of the "
-                    "Rust reference, which cannot be compiled in this image (no cargo/rustc)"}
+                    "Rust reference, which cannot be compiled in this image (no cargo/rustc); OpenMP threads = host cores, "
+                    "set explicitly"}
     print(json.dumps(line), flush=True)
 
 
 # ---- our arm --------------------------------------------------------------------------------------------------
+class OwBench:
+    """One OW workload on this rank: scene resident, partial / frame buffers, the step function for N ranks."""
+
+    def __init__(self, ctx, wl, spp, world_size, rank, dev):
+        import torch
+        from rendering_learning_b200 import dist as rd
+        from rendering_learning_b200 import ow
+        self.ctx, self.wl, self.world_size, self.rank, self.rd = ctx, wl, world_size, rank, rd
+        self.world = wl["world"]()
+        self.params = wl["params"]()
+        if spp:
+            self.params.samples_per_pixel = spp
+        self.desc = ow.lower_world(self.world)
+        self.cam = self.params.abi()
+        ctx.scene_upload(self.desc)
+        self.W, self.H, self.nc = self.cam.image_width, ctx.ow_image_height(self.cam), ctx.ow_num_chunks(self.cam)
+        self.samples = self.W * self.H * self.params.samples_per_pixel
+        self.out_bytes = self.H * self.W * 3 * 4
+        self.frame = torch.zeros((self.H, self.W, 3), dtype=torch.float32, device=dev)
+        self.partial_bytes = self.nc * self.H * self.W * 16
+        self.partial = None
+        self.stream = rd.current_stream_handle()
+        self.mgpu = os.environ.get("RL_MGPU", "fused") if world_size > 1 else "single"
+        if world_size == 1 or self.mgpu != "fused":
+            self.partial = torch.zeros((self.nc, self.H, self.W, 4), dtype=torch.float32, device=dev)
+        self.shared = world_size > 1 and rd.setup_shared_queue(ctx, self.partial_bytes if self.mgpu == "fused" else 0)
+        self.last_slot = None
+
+    def instrumented(self):
+        import torch
+        p = self.partial
+        if p is None:
+            p = torch.zeros((self.nc, self.H, self.W, 4), dtype=torch.float32, device=self.frame.device)
+        self.ctx.set_instrumented(True)
+        torch.cuda.synchronize()
+        st = self.ctx.render_ow_device(self.cam, 0, [(0, 0, self.W, self.H, 0, self.nc)], p.data_ptr(), self.stream).as_dict()
+        self.ctx.set_instrumented(False)
+        return st
+
+    def step(self):
+        """returns the number of kernels this rank launched"""
+        if self.world_size == 1:
+            self.ctx.render_ow_device(self.cam, 0, [(0, 0, self.W, self.H, 0, self.nc)], self.partial.data_ptr(), self.stream, sync=False)
+            self.ctx.ow_reduce_device(self.cam, self.partial.data_ptr(), self.frame.data_ptr(), self.stream)
+            return 2
+        if self.mgpu == "fused":
+            self.last_slot = self.rd.render_ow_fused(self.ctx, self.cam, 0, self.frame, self.nc, self.H, self.W)
+            return 2 if self.rank == 0 else 1
+        self.rd.render_ow_shared_queue(self.ctx, self.cam, 0, self.partial, self.frame, self.nc, self.H, self.W)
+        return 2 if self.rank == 0 else 1
+
+    def check(self):
+        if self.world_size > 1 and self.mgpu == "fused" and self.rank == 0 and self.last_slot is not None:
+            self.rd.check_fused_complete(self.ctx, self.cam, self.last_slot, self.nc, self.H, self.W)
+
+    def kernel_probe_ms(self):
+        import torch
+        p = self.partial
+        if p is None:
+            p = torch.zeros((self.nc, self.H, self.W, 4), dtype=torch.float32, device=self.frame.device)
+        return self.ctx.render_ow_device(self.cam, 0, [(0, 0, self.W, self.H, 0, self.nc)], p.data_ptr(), self.stream).kernel_ms
+
+    def parallelism(self):
+        if self.world_size == 1:
+            return "1 rank, persistent CTAs, path slots + ready/done rings in shared memory"
+        how = ("partial sums stored straight into rank 0's HBM over NVLink (fused gather), one 4-byte NCCL all-reduce "
+               "per render as the closing rendezvous, alternating queue slots (no pre-launch rendezvous)"
+               if self.mgpu == "fused" else "NCCL sum-gather to rank 0")
+        return (f"one persistent launch per GPU; CTAs pop (pixel x sample-chunk) batches from ONE counter in rank 0's HBM with "
+                f"system-scope atomics over NVLink (CUDA IPC); {how}, {self.world_size} ranks")
+
+
+class RtcBench:
+    def __init__(self, ctx, wl, world_size, rank, dev):
+        import torch
+        from rendering_learning_b200 import dist as rd
+        self.ctx, self.wl, self.world_size, self.rank, self.rd = ctx, wl, world_size, rank, rd
+        self.scene = wl["scene"]()
+        self.desc = self.scene.world.lower()
+        self.cam = self.scene.camera.abi()
+        ctx.scene_upload(self.desc)
+        self.W, self.H = self.cam.hsize, self.cam.vsize
+        self.samples = self.W * self.H
+        self.out_bytes = self.H * self.W * 3 * 4
+        self.frame = torch.zeros((self.H, self.W, 3), dtype=torch.float32, device=dev)
+        self.stream = rd.current_stream_handle()
+        self.jobs = (rd.make_jobs(self.W, self.H, 1, rows_per_job=max(4, self.H // (world_size * 4)))
+                     if world_size > 1 else [(0, 0, self.W, self.H, 0, 1)])
+        self.counter = 0
+
+    def instrumented(self):
+        import torch
+        self.ctx.set_instrumented(True)
+        torch.cuda.synchronize()
+        st = self.ctx.render_rtc_device(self.cam, 1, [(0, 0, self.W, self.H, 0, 1)], self.frame.data_ptr(), self.stream).as_dict()
+        self.ctx.set_instrumented(False)
+        return st
+
+    def step(self):
+        self.counter += 1
+        if self.world_size == 1:
+            self.ctx.render_rtc_device(self.cam, 1, self.jobs, self.frame.data_ptr(), self.stream, sync=False)
+            return 1
+        return len(self.rd.render_rtc_distributed(self.ctx, self.cam, 1, self.jobs, self.frame, f"s{self.counter}"))
+
+    def check(self):
+        pass
+
+    def kernel_probe_ms(self):
+        return self.ctx.render_rtc_device(self.cam, 1, [(0, 0, self.W, self.H, 0, 1)], self.frame.data_ptr(), self.stream).kernel_ms
+
+    def parallelism(self):
+        return (f"{len(self.jobs)} static interleaved row bands, NCCL sum-gather to rank 0, {self.world_size} ranks"
+                if self.world_size > 1 else "1 rank, one launch")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -247,152 +383,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op) -> float:
         if world_size == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if world_size == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX)
 
-    stream = rd.current_stream_handle()
-    if wl["kind"] == "ow":
-        world = wl["world"]()
-        params = wl["params"]()
-        if args.spp:
-            params.samples_per_pixel = args.spp
-        desc = ow.lower_world(world)
-        cam = params.abi()
-        ctx.scene_upload(desc)
-        W, H, nc = cam.image_width, ctx.ow_image_height(cam), ctx.ow_num_chunks(cam)
-        partial = torch.zeros((nc, H, W, 4), dtype=torch.float32, device=dev)
-        frame = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-        jobs = rd.jobs_for(W, H, nc, world_size) if world_size > 1 else [(0, 0, W, H, 0, nc)]
-        samples = W * H * params.samples_per_pixel
-        out_bytes = H * W * 3 * 4
-        # instrumented pass (same seed): rays and unit counts of one step
-        ctx.set_instrumented(True)
-        torch.cuda.synchronize()
-        st_i = ctx.render_ow_device(cam, 0, [(0, 0, W, H, 0, nc)], partial.data_ptr(), stream).as_dict() if rank == 0 else None
-        ctx.set_instrumented(False)
-        counter = [0]
-
-        # RL_MGPU: "fused"  = NVLink-atomic queue + partial sums stored straight into rank 0's HBM (default)
-        #          "device" = NVLink-atomic queue, NCCL sum-gather of the partial sums
-        #          "store"  = c10d-store job queue, NCCL sum-gather
-        mgpu = os.environ.get("RL_MGPU", "fused")
-        shared = world_size > 1 and mgpu in ("device", "fused") and rd.setup_shared_queue(
-            ctx, partial.numel() * 4 if mgpu == "fused" else 0)
-
-        def step(i):
-            counter[0] += 1
-            if shared and mgpu == "fused":
-                rd.render_ow_fused(ctx, cam, 0, frame, nc, H, W)
-                return [0]
-            if shared:
-                rd.render_ow_shared_queue(ctx, cam, 0, partial, frame, nc, H, W)
-                return [0]
-            return rd.render_ow_distributed(ctx, cam, 0, jobs, partial, frame, f"s{i}_{counter[0]}")
-
-        def kernel_probe():
-            # the dominant kernel alone, whole frame, on this stream (roofline numerator / denominator)
-            return ctx.render_ow_device(cam, 0, [(0, 0, W, H, 0, nc)], partial.data_ptr(), stream)
-
-        def e2e_step():
-            out = e2e_out
-            t0 = time.perf_counter()
-            d2 = ow.lower_world(world)  # the public call lowers the tree every time
-            d2.freeze()
-            t1 = time.perf_counter()
-            ctx.scene_upload(d2)
-            t2 = time.perf_counter()
-            if world_size == 1:
-                ctx.render_ow(cam, 0, out=out)
-            else:
-                step(10_000 + counter[0])
-                if rank == 0:
-                    e2e_pinned.copy_(frame, non_blocking=False)
-            t3 = time.perf_counter()
-            e2e_phases.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3])
-            return desc.nbytes(), out_bytes
-    else:
-        scene = wl["scene"]()
-        desc = scene.world.lower()
-        cam = scene.camera.abi()
-        ctx.scene_upload(desc)
-        W, H = cam.hsize, cam.vsize
-        frame = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-        jobs = rd.make_jobs(W, H, 1, rows_per_job=max(4, H // (world_size * 4))) if world_size > 1 else [(0, 0, W, H, 0, 1)]
-        samples = W * H
-        out_bytes = H * W * 3 * 4
-        ctx.set_instrumented(True)
-        torch.cuda.synchronize()
-        st_i = ctx.render_rtc_device(cam, 1, [(0, 0, W, H, 0, 1)], frame.data_ptr(), stream).as_dict() if rank == 0 else None
-        ctx.set_instrumented(False)
-        counter = [0]
-        shared, mgpu = False, "static"
-
-        def step(i):
-            counter[0] += 1
-            return rd.render_rtc_distributed(ctx, cam, 1, jobs, frame, f"s{i}_{counter[0]}")
-
-        def kernel_probe():
-            return ctx.render_rtc_device(cam, 1, [(0, 0, W, H, 0, 1)], frame.data_ptr(), stream)
-
-        def e2e_step():
-            t0 = time.perf_counter()
-            d2 = scene.world.lower()
-            d2.freeze()
-            t1 = time.perf_counter()
-            ctx.scene_upload(d2)
-            t2 = time.perf_counter()
-            if world_size == 1:
-                ctx.render_rtc(cam, 1, out=e2e_out)
-            else:
-                step(10_000 + counter[0])
-                if rank == 0:
-                    e2e_pinned.copy_(frame, non_blocking=False)
-            t3 = time.perf_counter()
-            e2e_phases.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3])
-            return desc.nbytes(), out_bytes
-
-    e2e_pinned = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
-    e2e_phases = []
-    e2e_out = e2e_pinned.numpy()
-
-    # ---- warm-up ----
-    for i in range(args.warmup):
-        step(-1 - i)
+    def timed_steps(b, n_warm, n_steps):
+        """W untimed steps, then EXACTLY K steps back to back between two events, barrier + synchronize on both sides;
+        the L2 is flushed between steps (a 256 MiB write on the same stream, 0.04 ms, inside the timed region).
+        Returns (ms per step = max over ranks, kernels launched over all ranks, wall seconds)."""
+        for _ in range(n_warm):
+            b.step()
         ctx.synchronize()
-    # ---- timed region: EXACTLY K steps, device-timed per step (the L2 flush between steps is outside) ----
+        b.check()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(n_steps):
+            flush.fill_(i & 0xFF)
+            launches += b.step() + 1
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ctx.synchronize()
+        b.check()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / n_steps
+        return ms, int(reduce_ranks(float(launches), dist.ReduceOp.SUM)), wall
+
+    B = OwBench(ctx, wl, args.spp, world_size, rank, dev) if wl["kind"] == "ow" else RtcBench(ctx, wl, world_size, rank, dev)
+    st_i = B.instrumented() if rank == 0 else None
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches = 0
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # evict L2 between timed iterations
-        if world_size > 1:
-            dist.barrier()
-        evs[i][0].record()
-        mine = step(i)
-        evs[i][1].record()
-        launches += len(mine) + (1 if (rank == 0 and wl["kind"] == "ow") else 0)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    ctx.synchronize()
-    step_ms = [max_over_ranks(a.elapsed_time(b)) for a, b in evs]
-    ms_per_step = float(np.mean(step_ms))
+    ms_per_step, total_launches, t_wall = timed_steps(B, args.warmup, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    total_launches = int(sum_over_ranks(float(launches)))
 
     # ---- dominant kernel alone (roofline) ----
     peaks = ctx.measure_peaks() if rank == 0 else None
@@ -401,34 +433,81 @@ def main():
         for _ in range(3):
             flush.fill_(1)
             torch.cuda.synchronize()
-            k_ms.append(kernel_probe().kernel_ms)
+            k_ms.append(B.kernel_probe_ms())
     barrier()
 
-    # ---- e2e through the public API ----
-    e2e_n = max(1, min(args.steps, 3))
-    e2e_step()
-    ctx.synchronize()
-    barrier()
-    e2e_phases.clear()
-    t0 = time.perf_counter()
-    for _ in range(e2e_n):
-        h2d, d2h = e2e_step()
-    ctx.synchronize()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_n)
+    # ---- e2e through the public API: the literal Camera.render(world) call, pageable output ----
+    e2e_phases = []
+
+    def e2e_step(prepared):
+        t0 = time.perf_counter()
+        if wl["kind"] == "ow":
+            if world_size == 1:
+                cv = ow.Camera.new(B.params).render(B.desc if prepared else B.world, ctx=ctx)
+            else:
+                cv = rd.camera_render_ow(ow.Camera.new(B.params), B.desc if prepared else B.world, ctx, B)
+        else:
+            if world_size == 1:
+                cv = B.scene.camera.render(B.desc if prepared else B.scene.world, ctx=ctx)
+            else:
+                cv = rd.camera_render_rtc(B.scene.camera, B.desc if prepared else B.scene.world, ctx, B)
+        e2e_phases.append((time.perf_counter() - t0) * 1e3)
+        return cv
+
+    def e2e_time(prepared):
+        n = max(1, min(args.steps, 3))
+        e2e_step(prepared)
+        ctx.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            e2e_step(prepared)
+        ctx.synchronize()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) / n), n
+
+    e2e_s, e2e_n = e2e_time(False)
+    e2e_prep_s, _ = e2e_time(True)
+
+    # ---- secondary workloads (the metric names the spot mesh and the teapot beside the cover scene) ----
+    secondary = []
+    if not args.no_secondary and args.workload == "C4" and not args.spp:
+        all_wl = workloads()
+        sec_keys = ["C5"] + (["C3"] if world_size == 1 else [])
+        for key in sec_keys:
+            w2 = all_wl[key]
+            B2 = OwBench(ctx, w2, 0, world_size, rank, dev) if w2["kind"] == "ow" else RtcBench(ctx, w2, world_size, rank, dev)
+            s2 = B2.instrumented() if rank == 0 else None
+            sampler2 = ClockSampler(local)
+            if rank == 0:
+                sampler2.start()
+            ms2, l2, _ = timed_steps(B2, 3, max(2, min(args.steps, 3)) if key == "C5" else max(args.steps, 10))
+            ck2 = sampler2.stop() if rank == 0 else None
+            if rank == 0:
+                fl2, _ = algorithmic(w2["kind"], s2, B2.samples)
+                k2 = float(np.mean([B2.kernel_probe_ms() for _ in range(2)]))
+                secondary.append({"workload": w2["name"], "metric": metric_name(w2), "value": s2["rays"] / (ms2 * 1e-3) / 1e6,
+                                  "unit": "Mrays/s", "ms_per_step": ms2, "samples_per_s": B2.samples / (ms2 * 1e-3),
+                                  "n_gpus": world_size, "clocks": ck2, "gpu_launches": l2,
+                                  "roofline": {"bound": "issue", "achieved": fl2 / (k2 * 1e-3) / 1e12, "peak": peaks["fp32_tflops"],
+                                               "unit": "TFLOP/s", "frac": fl2 / (k2 * 1e-3) / 1e12 / peaks["fp32_tflops"],
+                                               "kernel_ms": k2, "ncu": ncu_summary(key) or None}})
+            del B2
+        # the headline scene goes back on the device (the e2e path above already did the same every step)
+        ctx.scene_upload(B.desc)
 
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
         return
 
-    # the image of the last timed step: identical for every GPU count / tile schedule (compare across --gpus runs)
+    # the image of the last timed step: identical for every GPU count / schedule (compare across --gpus runs)
     import hashlib
     torch.cuda.synchronize()
-    frame_md5 = hashlib.md5(frame.detach().cpu().numpy().tobytes()).hexdigest()
+    frame_md5 = hashlib.md5(B.frame.detach().cpu().numpy().tobytes()).hexdigest()
     rays = st_i["rays"]
     value = rays / (ms_per_step * 1e-3) / 1e6
-    fl, by = algorithmic(wl["kind"], st_i, samples)
+    fl, by = algorithmic(wl["kind"], st_i, B.samples)
     kms = float(np.mean(k_ms))
     measured = {}
     try:
@@ -437,70 +516,44 @@ def main():
         pass
     hbm_peak = measured.get("hbm_gbs", 6650.0)
     ach_tf = fl / (kms * 1e-3) / 1e12
-    hbm_alg = samples * 0 + out_bytes + (partial.numel() * 4 if wl["kind"] == "ow" else 0)
-    prof = {}
-    pj = os.path.join(ROOT, "profiles", f"ncu_{args.workload}.json")
-    if os.path.exists(pj):
-        prof = json.load(open(pj))
-    roofline = {"bound": "fp32", "achieved": ach_tf, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
+    hbm_alg = B.out_bytes + (B.partial_bytes if wl["kind"] == "ow" else 0)
+    prof = ncu_summary(args.workload)
+    roofline = {"bound": "issue", "bound_note": "instruction issue x SIMT lane utilisation; neither HBM nor tensor cores bound this path "
+                                                 "(SURVEY.md §8d); achieved/peak/frac = algorithmic FP32 flops vs the measured FP32 FMA peak",
+                "achieved": ach_tf, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
                 "frac": ach_tf / peaks["fp32_tflops"], "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_ow_render5" if wl["kind"] == "ow" else "k_rtc_render", "kernel_ms": kms,
-                "traffic_source": prof.get("source"),
+                "kernel": "k_ow_render6" if wl["kind"] == "ow" else "k_rtc_render", "kernel_ms": kms,
                 "flops_per_launch": fl, "peak_source": "measured live (rl_measure_peaks: FMA chains, all SMs)",
-                "l2": {"achieved": by / (kms * 1e-3) / 1e9, "peak": peaks["l2_gbs"], "unit": "GB/s",
-                       "frac": by / (kms * 1e-3) / 1e9 / peaks["l2_gbs"], "bytes_per_launch": by},
+                "ncu": prof or None,
+                "l1_algorithmic": {"bytes_per_launch": by, "achieved": by / (kms * 1e-3) / 1e9, "unit": "GB/s",
+                                   "note": "node / primitive fetches; ~all of them hit L1 (see ncu.l1_hit_pct), so this is NOT L2 traffic"},
                 "hbm": {"achieved": hbm_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": hbm_alg / (kms * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": hbm_alg,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in measured else "fallback 6650"},
                 "counters": {k: st_i[k] for k in ("rays", "node_visits", "prim_tests", "tri_tests", "shades")}}
-    line = {"metric": f"Mrays/s (device-timed), {wl['name']}", "value": value, "unit": "Mrays/s",
+    line = {"metric": metric_name(wl), "value": value, "unit": "Mrays/s", "timing": "device (CUDA events around K back-to-back steps)",
             "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "image": [W, H], "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": (("one persistent launch per GPU; warps pop (pixel x sample-chunk) items from ONE counter in "
-                                        "rank 0's HBM with system-scope atomics over NVLink (CUDA IPC); " +
-                                        ("partial sums stored straight into rank 0's HBM over NVLink (fused gather)"
-                                         if mgpu == "fused" else "NCCL sum-gather to rank 0")
-                                        if (wl["kind"] == "ow" and shared)
-                                        else f"{len(jobs)} tile x sample-chunk jobs from a c10d-store queue, NCCL sum-gather to rank 0") +
-                                       f", {world_size} ranks") if world_size > 1 else "1 rank, persistent warps"},
-            "samples_per_s": samples / (ms_per_step * 1e-3), "rays_per_step": rays, "samples_per_step": samples,
-            "wall_s_timed_region": t_wall, "step_ms": step_ms, "frame_md5": frame_md5,
+            "config": {"workload": wl["name"], "image": [B.W, B.H], "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": B.parallelism()},
+            "samples_per_s": B.samples / (ms_per_step * 1e-3), "rays_per_step": rays, "samples_per_step": B.samples,
+            "wall_s_timed_region": t_wall, "frame_md5": frame_md5,
             "clocks": clocks, "gpu_launches": total_launches,
-            "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_n,
-                    "phases_ms_rank0": {"lower_tree": float(np.mean([p[0] for p in e2e_phases])),
-                                        "scene_upload": float(np.mean([p[1] for p in e2e_phases])),
-                                        "render_and_d2h": float(np.mean([p[2] for p in e2e_phases]))},
-                    "path": "Camera.render: lower tree -> rl_scene_upload (flatten, H2D, LBVH build) -> render -> D2H (pinned)"},
+            "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(B.desc.nbytes()),
+                    "d2h_bytes_per_step": int(B.out_bytes), "ms_per_step": e2e_s * 1e3, "steps": e2e_n,
+                    "host_buffer": "pageable (numpy), converted to the f64 Canvas",
+                    "path": "Camera.render(world): lower the object tree -> rl_scene_upload (flatten, H2D, LBVH build) -> render -> D2H",
+                    "prepared": {"value": rays / e2e_prep_s / 1e6, "ms_per_step": e2e_prep_s * 1e3,
+                                 "path": "Camera.render(scene_desc): the caller keeps the lowered description"}},
             "roofline": roofline}
-
-    if world_size == 1 and not args.no_secondary and args.workload == "C4":
-        # the metric names the teapot beside the cover scene: measure C3 the same way
-        sc3 = workloads()["C3"]["scene"]()
-        ctx.scene_upload(sc3.world.lower())
-        c3 = sc3.camera.abi()
-        f3 = torch.zeros((c3.vsize, c3.hsize, 3), dtype=torch.float32, device=dev)
-        torch.cuda.synchronize()
-        ctx.set_instrumented(True)
-        s3 = ctx.render_rtc_device(c3, 1, [(0, 0, c3.hsize, c3.vsize, 0, 1)], f3.data_ptr(), stream).as_dict()
-        ctx.set_instrumented(False)
-        t3 = []
-        for i in range(args.warmup + args.steps):
-            flush.fill_(i & 0xFF)
-            torch.cuda.synchronize()
-            t3.append(ctx.render_rtc_device(c3, 1, [(0, 0, c3.hsize, c3.vsize, 0, 1)], f3.data_ptr(), stream).kernel_ms)
-        t3 = float(np.mean(t3[args.warmup:]))
-        fl3, by3 = algorithmic("rtc", s3, c3.hsize * c3.vsize)
-        line["secondary"] = {"workload": workloads()["C3"]["name"], "value": s3["rays"] / (t3 * 1e-3) / 1e6,
-                             "unit": "Mrays/s", "ms_per_step": t3, "samples_per_s": c3.hsize * c3.vsize / (t3 * 1e-3),
-                             "roofline": {"bound": "fp32", "achieved": fl3 / (t3 * 1e-3) / 1e12, "peak": peaks["fp32_tflops"],
-                                          "unit": "TFLOP/s", "frac": fl3 / (t3 * 1e-3) / 1e12 / peaks["fp32_tflops"]}}
+    if secondary:
+        line["secondary"] = secondary
 
     if world_size == 1 and not args.no_cpu:
-        v, sps, what, dt = cpu_run(wl, 15.0)
+        cores = host_cores()
+        v, sps, what, dt = cpu_run(wl, 15.0, cores)
         line["cpu_baseline"] = {"value": v if v is not None else sps / 1e6, "unit": "Mrays/s" if v is not None else "Mpixels/s",
-                                "cores": host_cores(), "kind": "port", "sample": what, "seconds": dt,
+                                "cores": cores, "threads": cores, "kind": "port", "sample": what, "seconds": dt,
                                 "samples_per_s": sps}
     emit(line)
     if world_size > 1:

@@ -170,6 +170,35 @@ def ow_trace(desc, rays: np.ndarray, threads: int = 0):
     return node, t, uv
 
 
+def ow_trace_self(desc, rays: np.ndarray, self_nodes: np.ndarray, threads: int = 0):
+    """ow_trace for rays that start on a surface (self_nodes[i] = that leaf, -1 none): the oracle then applies the
+    device path's start-on-surface rule (oracle_ow.cpp tl_self_node) instead of relying on f64 + t_min = 1e-10."""
+    d = desc.freeze()
+    rays = np.ascontiguousarray(rays, np.float64).reshape(-1, 7)
+    sn = np.ascontiguousarray(self_nodes, np.int32).reshape(-1)
+    n = rays.shape[0]
+    node = np.zeros(n, np.int32)
+    t = np.zeros(n, np.float64)
+    uv = np.zeros((n, 2), np.float64)
+    rc = lib().orc_ow_trace_self(C.byref(d), _dp(rays), _ip(sn), C.c_uint64(n), _ip(node), _dp(t), _dp(uv), C.c_int(threads))
+    if rc != 0:
+        raise RuntimeError("orc_ow_trace_self failed")
+    return node, t, uv
+
+
+def ow_bounce_rays(desc, cam: A.rl_ow_camera, bounce: int):
+    """The reference's own ray at bounce `bounce` of every pixel's first sample: (rays [n,7] f64, self_nodes [n] —
+    -1 camera ray, -2 the path ended earlier)."""
+    d = desc.freeze()
+    h = ow_image_height(cam)
+    n = h * cam.image_width
+    rays = np.zeros((n, 7), np.float64)
+    sn = np.zeros(n, np.int32)
+    if lib().orc_ow_bounce_rays(C.byref(d), C.byref(cam), C.c_int(bounce), _dp(rays), _ip(sn)) != 0:
+        raise RuntimeError("orc_ow_bounce_rays failed")
+    return rays, sn
+
+
 def ow_tex_value(desc, tex: int, uvp: np.ndarray) -> np.ndarray:
     """Texture::value at rows (u, v, x, y, z)"""
     d = desc.freeze()

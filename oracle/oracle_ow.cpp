@@ -247,6 +247,14 @@ inline V3 mul(const M3& a, V3 v) {  // matrix.rs:42-60
 // with no stream attached (orc_ow_trace) a medium is never hit.
 static thread_local ChaCha8Rng* tl_medium_rng = nullptr;
 
+// TEST HOOK (orc_ow_trace_self only; -1 everywhere else, which leaves the restatement untouched).  The reference keeps a
+// scattered ray from re-hitting the surface it starts on with f64 and t_min = 1e-10 (camera.rs:242).  The f32 device
+// path cannot (its origin is ~1e-7 off the surface), so it states the same intent as a rule: a ray never re-hits the
+// PLANAR primitive it starts on, and takes only the FAR root of its own sphere, beyond 1e-4 radii.  When the parity
+// tests hand f32-rounded scattered rays to this oracle, the oracle must apply that rule too — otherwise it would
+// "hit" the start surface at t ~ 1e-8 whenever rounding pushed the origin inside.
+static thread_local int tl_self_node = -1;
+
 struct Scene;
 struct Obj {
     int kind, node, material = -1;
@@ -441,6 +449,7 @@ struct Scene {
 
     // Plane::hit_ab (flat/plane.rs:51-80) + Plane::hit (86-100)
     bool hit_plane(const Obj& o, const Ray& r, const Interval& rt, HitRecord* rec) const {
+        if (o.node == tl_self_node) return false;  // test hook, see tl_self_node
         double denom = dot(o.normal, r.direction);
         if (std::fabs(denom) < 1e-8) return false;
         double t = (o.d - dot(o.normal, r.origin)) / denom;
@@ -468,6 +477,11 @@ struct Scene {
                 double s = std::sqrt(disc);
                 double r_l = (-half_b - s) / a, r_u = (-half_b + s) / a;
                 double t;
+                if (o.node == tl_self_node) {  // test hook, see tl_self_node
+                    r_u = -2.0 * half_b / a;
+                    if (!(r_u > 1e-4 * std::fabs(o.radius) / std::sqrt(a)) || !rt.contains(r_u)) return false;
+                    t = r_u;
+                } else
                 if (rt.contains(r_l)) t = r_l;
                 else if (rt.contains(r_u)) t = r_u;
                 else return false;
@@ -803,6 +817,75 @@ int orc_ow_trace(const rl_scene_desc* desc, const double* rays, uint64_t n, int3
             if (uv) { uv[2 * i] = 0; uv[2 * i + 1] = 0; }
         }
     }
+    return 0;
+}
+
+// orc_ow_trace for rays that start on a surface: self_nodes[i] = the leaf node ray i starts on (-1 none); see tl_self_node
+int orc_ow_trace_self(const rl_scene_desc* desc, const double* rays, const int32_t* self_nodes, uint64_t n, int32_t* node,
+                      double* t, double* uv, int threads) {
+    if (!desc || desc->flavor != RL_FLAVOR_OW) return -1;
+    Scene sc(desc);
+    if (!sc.ok) return -1;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const double* r = rays + 7 * i;
+        Ray ray{v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), r[6]};
+        HitRecord h;
+        tl_self_node = self_nodes ? self_nodes[i] : -1;
+        const bool was_hit = sc.hit(*sc.root, ray, {1e-10, INF}, &h);
+        tl_self_node = -1;
+        if (was_hit) {
+            node[i] = h.node; t[i] = h.t;
+            if (uv) { uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
+        } else {
+            node[i] = -1; t[i] = INF;
+            if (uv) { uv[2 * i] = 0; uv[2 * i + 1] = 0; }
+        }
+    }
+    return 0;
+}
+
+// The reference's OWN ray at bounce `bounce` of every pixel's first sample (bounce 0 = the camera ray, 1 = the first
+// scattered ray, ...): get_ray, then `bounce` rounds of world.hit + Material::scatter with the reference's RNG stream
+// (camera.rs:161-170, 232-260).  rays: n*7 doubles; self_nodes[i] = the leaf the ray starts on (-1 for camera rays),
+// or -2 when the path ended before that bounce (miss, absorbed, light).
+int orc_ow_bounce_rays(const rl_scene_desc* desc, const rl_ow_camera* cam, int bounce, double* rays, int32_t* self_nodes) {
+    if (!desc || desc->flavor != RL_FLAVOR_OW || bounce < 0) return -1;
+    Scene sc(desc);
+    if (!sc.ok) return -1;
+    Camera c(cam);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (int y = 0; y < c.height; y++)
+        for (int x = 0; x < c.width; x++) {
+            ChaCha8Rng rng(c.p.seed);
+            rng.set_stream((uint64_t)x * (uint64_t)c.width + (uint64_t)y);
+            Ray r = c.get_ray(rng, x, y);
+            int self = -1;
+            for (int b = 0; b < bounce && self != -2; b++) {
+                HitRecord h;
+                tl_medium_rng = &rng;
+                const bool was_hit = sc.hit(*sc.root, r, {1e-10, INF}, &h);
+                tl_medium_rng = nullptr;
+                V3 att;
+                Ray sr;
+                if (was_hit && sc.scatter(h.material, rng, r, h, &att, &sr)) {
+                    r = sr;
+                    self = h.node;
+                } else {
+                    self = -2;
+                }
+            }
+            const size_t k = (size_t)y * c.width + x;
+            double* o = rays + 7 * k;
+            o[0] = r.origin.x; o[1] = r.origin.y; o[2] = r.origin.z;
+            o[3] = r.direction.x; o[4] = r.direction.y; o[5] = r.direction.z; o[6] = r.time;
+            self_nodes[k] = self;
+        }
     return 0;
 }
 

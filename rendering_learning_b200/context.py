@@ -65,6 +65,12 @@ class Context:
         return {"fp32_tflops": a.value, "l2_gbs": b.value, "hbm_gbs": c.value}
 
     def scene_upload(self, desc: SceneDesc):
+        """rl_scene_upload.  A frozen SceneDesc is an immutable snapshot, so uploading the SAME description object again
+        is a no-op: a caller that keeps its lowered scene (`Camera.render(scene_desc)`) pays for flattening, H2D and the
+        LBVH build once."""
+        if self._scene is desc and desc._frozen is not None:
+            return
+        self._scene = None
         d = desc.freeze()
         self._check(self.lib.rl_scene_upload(self.h, C.byref(d)))
         self._scene = desc

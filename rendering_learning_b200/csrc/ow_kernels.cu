@@ -1015,7 +1015,8 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
                                 SL(ACCX, id) = SL(ACCY, id) = SL(ACCZ, id) = 0.0f;
                                 has_item = true;
                             } else {
-                                requeue = true;  // a padded slot outside the rectangle: try again next round
+                                requeue = true;  // a padded slot outside the rectangle: nothing to render, try again next round
+                                retired++;       // ... but it IS a work item of the job list (rl_ow_job_items counts padded slots)
                             }
                         }
                     } else if (dry) {

@@ -79,6 +79,8 @@ def current_stream_handle() -> int:
     """cudaStream_t of torch's current stream.  The C ABI reads 0 as "the ctx's own stream", so the legacy
     default stream is passed as cudaStreamLegacy (0x1) to keep the launch on the stream torch events see."""
     import torch
+    if not torch.cuda.is_available():
+        return 0  # CPU-side tests of the protocol (gloo): there is no stream
     h = torch.cuda.current_stream().cuda_stream
     return h if h else 1
 
@@ -218,3 +220,40 @@ def render_rtc_distributed(ctx, cam, aa: int, jobs: Sequence[Job], frame, step_k
     if world > 1:
         dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
     return mine
+
+
+# ---- the drop-in call for one-process-per-GPU programs ---------------------------------------------------------------
+def camera_render_ow(camera, world, ctx, buffers):
+    """`Camera::render(world)` (OW/src/camera.rs:122-124) as a COLLECTIVE: every rank of an SPMD program calls it with the
+    same camera and world (each rank built the same scene), the ranks render it together, rank 0 gets the Canvas (the
+    others None).  Per call: lower the object tree (unless `world` is already a SceneDesc), rl_scene_upload on every rank,
+    one fused multi-GPU render, device -> pageable host copy and f64 Canvas on rank 0.
+    `buffers`: an object with .frame ([H, W, 3] f32 device tensor), .nc, .H, .W whose rank 0 ctx exported the queue and
+    partial-sum slots (setup_shared_queue)."""
+    from . import ow
+    from .desc import SceneDesc
+    rank, world_size = _rank_world()
+    sd = world if isinstance(world, SceneDesc) else ow.lower_world(world)
+    ctx.scene_upload(sd)
+    slot = render_ow_fused(ctx, camera.params.abi(), 0, buffers.frame, buffers.nc, buffers.H, buffers.W)
+    if rank != 0:
+        return None
+    check_fused_complete(ctx, camera.params.abi(), slot, buffers.nc, buffers.H, buffers.W)
+    sums = buffers.frame.cpu().numpy()  # pageable
+    return ow.Canvas(camera.params.samples_per_pixel, buffers.W, buffers.H, sums.astype("float64"))
+
+
+def camera_render_rtc(camera, world, ctx, buffers):
+    """`Camera::render(&world, &opts)` (RTC/src/scene/camera.rs:93) as a collective; see camera_render_ow."""
+    from . import rtc
+    from .desc import SceneDesc
+    rank, world_size = _rank_world()
+    sd = world if isinstance(world, SceneDesc) else world.lower()
+    ctx.scene_upload(sd)
+    buffers.counter += 1
+    render_rtc_distributed(ctx, camera.abi(), 1, buffers.jobs, buffers.frame, f"e{buffers.counter}")
+    if rank != 0:
+        return None
+    ctx.synchronize()
+    rgb = buffers.frame.cpu().numpy()
+    return rtc.Canvas(camera.hsize, camera.vsize, rgb.astype("float64"))

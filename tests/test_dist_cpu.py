@@ -84,3 +84,77 @@ def test_job_grids():
     assert all(j[1] % 4 == 0 for j in jobs)
     jobs = rd.jobs_for(3840, 2160, 1, world_size=1)
     assert sum((j[2] - j[0]) * (j[3] - j[1]) for j in jobs) == 3840 * 2160
+
+
+# ---- the fused multi-GPU protocol (alternating queue slots, one closing rendezvous) on CPU ----------------------------
+class _FakeCtx:
+    """records the C-ABI calls dist.render_ow_fused makes; `completed` plays the owner's completion counter"""
+
+    def __init__(self, rank, log):
+        self.rank, self.log, self.completed = rank, log, {0: 0, 1: 0}
+
+    def queue_reset(self, stream, slot):
+        self.log.append(("reset", slot))
+        self.completed[slot] = 0
+
+    def render_ow_shared(self, cam, first, jobs, d_partial, stream, slot):
+        assert d_partial == 0  # fused gather: the library picks the owner's buffer of this slot
+        self.log.append(("render", slot))
+        self.completed[slot] += 100
+
+    def ow_reduce_shared(self, cam, slot, out_ptr, stream):
+        self.log.append(("fold", slot))
+
+    def ow_job_items(self, cam, jobs):
+        return 100
+
+    def queue_completed(self, stream, slot):
+        return self.completed[slot]
+
+
+def _fused_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    log = []
+    ctx = _FakeCtx(rank, log)
+    rd._fused_state["render"] = 0
+    out = torch.zeros(4)
+    slots = []
+    for _ in range(3):
+        slot = rd.render_ow_fused(ctx, None, 0, out, 2, 8, 8)
+        slots.append(slot)
+        if rank == 0:
+            rd.check_fused_complete(ctx, None, slot, 2, 8, 8)
+    bad = None
+    if rank == 0:
+        ctx.completed[slots[-1]] = 99  # a rank that died: one item short
+        try:
+            rd.check_fused_complete(ctx, None, slots[-1], 2, 8, 8)
+        except RuntimeError as e:
+            bad = str(e)
+    q.put((rank, log, slots, bad))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_protocol_alternates_slots_and_detects_missing_items():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (log, slots, bad)) for r, log, slots, bad in (q.get(timeout=120) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    log0, slots0, bad0 = res[0]
+    log1, slots1, _ = res[1]
+    # rank 0: before rendering on slot s it resets the OTHER slot (for the next render), then folds slot s
+    assert log0 == [("reset", 1), ("render", 0), ("fold", 0), ("reset", 0), ("render", 1), ("fold", 1),
+                    ("reset", 1), ("render", 0), ("fold", 0)]
+    assert slots0 == [0, 1, 0]
+    # the peer only launches: no reset, no fold, same slot sequence
+    assert log1 == [("render", 0), ("render", 1), ("render", 0)] and slots1 == [None, None, None]
+    assert bad0 is not None and "99 of 100" in bad0

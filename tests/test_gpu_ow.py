@@ -45,6 +45,7 @@ EXTRA_CASES = {
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_hit_ids_and_t_on_reference_camera_rays(ctx, oracle, name):
+    """rl_trace_batch runs the render kernel's own traversal (see test_gpu_ow_production.py for bounces 1 and 2)"""
     world, params = CASES[name]()
     desc = ow.lower_world(world)
     ctx.scene_upload(desc)

@@ -1,0 +1,260 @@
+"""Parity of the PRODUCTION OW loop on the B200 (round-1 verdict, weak 1 / missing 6).
+
+* rl_trace_batch for OW scenes runs through the render kernel itself (k_ow_render6 in trace mode: ready / done rings,
+  big list at ray start, unit directions, the scale-aware t_min, the start-on-surface rule, node steps, leaf rounds), so
+  the hit-id checks below exercise the loop that renders — on the reference's own rays at bounce 0, 1 and 2.
+* every scheduling option of the kernel gives the bit-identical image, and round 1's kernel (v5) the same bits again.
+* rays with exactly zero direction components (ADVICE: inf * 0 in the FMA slab test) hit what the oracle hits.
+* oracle-vs-device images at BASELINE.json's sizes, and a t-test for bias per first-hit material.
+"""
+import numpy as np
+import pytest
+
+from rendering_learning_b200 import ow, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+
+
+CASES = {
+    "test_scene": lambda: scenes.ow_test_scene(),
+    "C4_cover": lambda: (scenes.ow_cover_world(), scenes.ow_cover_params(image_width=300, samples_per_pixel=16)),
+    "C5_cow": lambda: (scenes.ow_cow_world(), scenes.ow_cow_params(image_width=160, samples_per_pixel=16)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("bounce", [0, 1, 2])
+def test_production_traversal_hit_ids_on_the_references_own_rays(ctx, oracle, name, bounce):
+    """OW/src/camera.rs:232-260, bvh.rs:79-90: the reference's ray at bounce k of every pixel's first sample (its own RNG
+    stream, its own scatter), rounded to f32 once, traced by the oracle and by the render kernel's traversal.  Scattered
+    rays start ON a surface: both sides apply the start-on-surface rule (include/rl_b200.h rl_trace_batch_ex)."""
+    world, params = CASES[name]()
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    rays64, self_nodes = oracle.ow_bounce_rays(desc, params.abi(), bounce)
+    keep = self_nodes != -2
+    assert keep.mean() > (0.9 if bounce == 0 else 0.2)
+    rays = rays64[keep].astype(np.float32)
+    sn = self_nodes[keep]
+    node, t, _ = oracle.ow_trace_self(desc, rays.astype(np.float64), sn)
+    hits = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6], rays[:, 6], self_nodes=sn)
+    mism = hits["node"] != node
+    # f32 vs f64 can only disagree on grazing rays: <= 1e-4 of the batch (0 measured on camera rays)
+    assert mism.mean() <= (1e-4 if bounce == 0 else 3e-4), (int(mism.sum()), len(node))
+    both = (~mism) & (node >= 0)
+    rel = np.abs(hits["t"][both].astype(np.float64) - t[both]) / np.maximum(np.abs(t[both]), 1e-30)
+    assert both.any() and np.quantile(rel, 0.999) <= 1e-4 and np.quantile(rel, 0.9999) <= 1e-3, (np.quantile(rel, 0.999), rel.max())
+    if bounce == 0:  # far-root / self rule is exercised from bounce 1 on; the big list from bounce 0
+        assert (node >= 0).mean() > 0.3
+
+
+def test_trace_without_self_nodes_equals_self_minus_one(ctx, oracle):
+    world, params = scenes.ow_test_scene()
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    rays = oracle.ow_camera_rays(params.abi()).astype(np.float32)[:5000]
+    a = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6], rays[:, 6])
+    b = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6], rays[:, 6], self_nodes=np.full(len(rays), -1, np.int32))
+    assert np.array_equal(a, b)
+    # unnormalised directions: t comes back in the CALLER's units
+    c = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6] * 4.0, rays[:, 6])
+    hit = a["node"] >= 0
+    assert np.array_equal(a["node"], c["node"]) and np.allclose(c["t"][hit] * 4.0, a["t"][hit], rtol=2e-6)
+
+
+def test_axis_aligned_directions(ctx, oracle):
+    """Directions with exactly zero components and origins off the axes: 1 / d is clamped to a finite value so that the
+    FMA slab test cannot produce inf - inf = NaN and silently miss the whole LBVH (device.cuh safe_rcp)."""
+    world = scenes.ow_cover_world()
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    rng = np.random.default_rng(3)
+    n = 60_000
+    o = np.stack([rng.uniform(-11, 11, n), rng.uniform(0.05, 3.0, n), rng.uniform(-11, 11, n)], axis=1)
+    d = np.zeros((n, 3))
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n), axis] = rng.choice([-1.0, 1.0], n)
+    third = n // 3  # the last third: one zero component only
+    k2 = (axis[-third:] + 1) % 3
+    d[np.arange(n - third, n), k2] = rng.uniform(-1, 1, third)
+    rays = np.concatenate([o, d, rng.uniform(0, 1, (n, 1))], axis=1).astype(np.float32)
+    node, t, _ = oracle.ow_trace(desc, rays.astype(np.float64))
+    hits = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6], rays[:, 6])
+    mism = hits["node"] != node
+    assert (node >= 0).mean() > 0.5  # most of these rays do hit spheres or the ground
+    assert mism.mean() <= 2e-4, (int(mism.sum()), n)
+    # the same through the image path: an axis-aligned camera above the scene centre looking straight down a coordinate axis
+    params = scenes.ow_cover_params(image_width=201, samples_per_pixel=4, max_depth=8)
+    params.lookfrom, params.lookat, params.defocus_angle = ow.Point3(0.0, 1.0, 12.0), ow.Point3(0.0, 1.0, 0.0), 0.0
+    sums, _ = ctx.render_ow(params.abi())
+    assert np.isfinite(sums).all()
+    centre = sums[:, 100] / 4  # the centre column has d.x == 0 up to jitter; it must see spheres, not only sky
+    assert centre.std() > 0.01
+
+
+OPTION_SETS = [
+    {},
+    {"ow.slots": 256},
+    {"ow.slots": 512, "ow.exit_min": 16},
+    {"ow.minb": 3, "ow.exit_min": 4, "ow.svc_lo": 8},
+    {"ow.leaf_min": 4, "ow.svc_lo": 24, "ow.ctas_per_sm": 2},
+    {"ow.variant": 5},
+    {"ow.variant": 5, "ow.svc_min": 8, "ow.leaf_min": 16},
+]
+RESET = {"ow.variant": 6, "ow.slots": 0, "ow.minb": 0, "ow.ctas_per_sm": 0, "ow.svc_lo": 0, "ow.exit_min": 0, "ow.leaf_min": 0,
+         "ow.svc_min": 0}
+
+
+@pytest.mark.parametrize("name", ["test_scene", "C4_cover", "C5_cow", "final_scene"])
+def test_every_schedule_and_round1_kernel_give_the_same_bits(ctx, name):
+    """The scheduling options move work between warps and rounds; per-path arithmetic and the order samples are folded
+    in are fixed, so the frame is bit-identical — including round 1's per-lane kernel (ow.variant = 5)."""
+    if name == "final_scene":
+        world, params = scenes.ow_final_scene(image_width=96, samples_per_pixel=24, max_depth=12)
+    else:
+        world, params = CASES[name]()
+        params.samples_per_pixel = 24
+    ctx.scene_upload(ow.lower_world(world))
+    ref = None
+    try:
+        for opts in OPTION_SETS:
+            for k, v in {**RESET, **opts}.items():
+                ctx.set_option(k, v)
+            sums, st = ctx.render_ow(params.abi())
+            assert st.overflow == 0
+            if ref is None:
+                ref = sums
+            assert np.array_equal(sums, ref), opts
+    finally:
+        for k, v in RESET.items():
+            ctx.set_option(k, v)
+    with pytest.raises(Exception):
+        ctx.set_option("ow.nonsense", 1)
+    with pytest.raises(Exception):
+        ctx.set_option("ow.minb", 2)
+
+
+def _first_hit_material_kind(oracle, desc, params, world_materials):
+    rays = oracle.ow_camera_rays(params.abi())
+    node, _, _ = oracle.ow_trace(desc, rays)
+    return node
+
+
+def test_no_bias_per_first_hit_material(ctx, oracle):
+    """Unbiasedness, tighter than a global mean: pixels are grouped by the material the reference's first-sample camera
+    ray hits (sky, ground Lambertian, Lambertian, Metal, Dielectric).  For every group the per-block differences of the
+    device and oracle means (64 random blocks, 64 spp each, independent RNGs) must be zero-mean: |t| < 4.5."""
+    world, params = scenes.ow_test_scene()
+    params.image_width = 240
+    params.samples_per_pixel = 64
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    cam = params.abi()
+    gpu, _ = ctx.render_ow(cam)
+    other = params.abi()
+    other.seed = 99
+    cpu, _ = oracle.ow_render(desc, other)
+    node, _, _ = oracle.ow_trace(desc, oracle.ow_camera_rays(cam))
+    d = desc.freeze()
+    kind = np.full(node.shape, -1)
+    for i in np.unique(node[node >= 0]):
+        kind[node == i] = d.materials[d.nodes[i].material].kind * 1000 + d.nodes[i].material
+    diff = (gpu.astype(np.float64) - cpu).reshape(-1, 3).mean(axis=1) / 64.0
+    level = (cpu.reshape(-1, 3).mean(axis=1) / 64.0)
+    rng = np.random.default_rng(0)
+    checked = 0
+    for kd in np.unique(kind):
+        idx = np.flatnonzero(kind == kd)
+        if len(idx) < 2000:
+            continue
+        rng.shuffle(idx)
+        blocks = np.array_split(idx, 64)
+        m = np.array([diff[b].mean() for b in blocks])
+        tstat = m.mean() / (m.std(ddof=1) / np.sqrt(len(m)) + 1e-12)
+        rel = abs(m.mean()) / max(level[idx].mean(), 1e-6)
+        assert abs(tstat) < 4.5 or rel < 2e-3, (int(kd), float(tstat), float(rel))
+        checked += 1
+    assert checked >= 4
+
+
+def test_psnr_c4_at_baseline_size(ctx, oracle):
+    """BASELINE C4 geometry, 1200x675 (SURVEY §8c rule at the full frame): device @16 spp vs oracle @128 spp against
+    the oracle's own seed-to-seed PSNR at 16 spp."""
+    world, params = scenes.ow_cover_world(), scenes.ow_cover_params(samples_per_pixel=16)
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    sums, st = ctx.render_ow(params.abi())
+    assert sums.shape == (675, 1200, 3)
+    hi = params.abi()
+    hi.seed, hi.samples_per_pixel = 777, 128
+    o_hi, _ = oracle.ow_render(desc, hi)
+    other = params.abi()
+    other.seed = 12345
+    o_other, _ = oracle.ow_render(desc, other)
+    ref = ow.Canvas(128, 1200, 675, o_hi).to_u8()
+    p_gpu = psnr(ow.Canvas(16, 1200, 675, sums).to_u8(), ref)
+    p_cpu = psnr(ow.Canvas(16, 1200, 675, o_other).to_u8(), ref)
+    assert p_gpu >= p_cpu - 0.5, (p_gpu, p_cpu)
+    m_gpu, m_hi = sums.mean() / 16, o_hi.mean() / 128
+    assert abs(m_gpu - m_hi) <= 0.004 * m_hi, (m_gpu, m_hi)
+
+
+def test_psnr_c5_at_960(ctx, oracle):
+    """BASELINE C5 scene at 960x540 (a quarter of the 4K frame in each direction; the oracle needs ~40 s here and would
+    need 10 minutes at 3840): device @8 spp vs oracle @64 spp."""
+    world, params = scenes.ow_cow_world(), scenes.ow_cow_params(image_width=960, samples_per_pixel=8)
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    sums, st = ctx.render_ow(params.abi())
+    assert sums.shape == (540, 960, 3)
+    hi = params.abi()
+    hi.seed, hi.samples_per_pixel = 777, 64
+    o_hi, _ = oracle.ow_render(desc, hi)
+    other = params.abi()
+    other.seed = 12345
+    o_other, _ = oracle.ow_render(desc, other)
+    ref = ow.Canvas(64, 960, 540, o_hi).to_u8()
+    p_gpu = psnr(ow.Canvas(8, 960, 540, sums).to_u8(), ref)
+    p_cpu = psnr(ow.Canvas(8, 960, 540, o_other).to_u8(), ref)
+    assert p_gpu >= p_cpu - 0.5, (p_gpu, p_cpu)
+    m_gpu, m_hi = sums.mean() / 8, o_hi.mean() / 64
+    assert abs(m_gpu - m_hi) <= 0.01 * m_hi, (m_gpu, m_hi)
+
+
+def test_multi_gpu_ctx_matches_single(ctx):
+    """rl_create_multi on the GPUs this box has (1 on the default test box: the group path degenerates to the plain one;
+    `gpurun --gpus 2` exercises the real thing): bit-identical frames for OW and RTC."""
+    import torch
+    from rendering_learning_b200 import Context
+    n = min(torch.cuda.device_count(), 8)
+    multi = Context(list(range(n)))
+    try:
+        assert multi.device_count() == n
+        world, params = scenes.ow_test_scene()
+        params.samples_per_pixel = 20
+        desc = ow.lower_world(world)
+        ctx.scene_upload(desc)
+        multi.scene_upload(desc)
+        a, _ = ctx.render_ow(params.abi())
+        b, st = multi.render_ow(params.abi())
+        assert np.array_equal(a, b) and st.kernel_launches == (n if n > 1 else 1) + 1
+        ua, _ = ctx.render_ow_u8(params.abi())
+        ub, _ = multi.render_ow_u8(params.abi())
+        assert np.array_equal(ua, ub)
+        sc = scenes.rtc_mirror_scene(301, 203)
+        d2 = sc.world.lower()
+        ctx.scene_upload(d2)
+        multi.scene_upload(d2)
+        ra, _ = ctx.render_rtc(sc.camera.abi(), 1)
+        rb, _ = multi.render_rtc(sc.camera.abi(), 1)
+        assert np.array_equal(ra, rb)
+        r8a, _ = ctx.render_rtc_u8(sc.camera.abi(), 1)
+        r8b, _ = multi.render_rtc_u8(sc.camera.abi(), 1)
+        assert np.array_equal(r8a, r8b)
+    finally:
+        multi.close()
