@@ -171,14 +171,15 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
         float4 a = np[0], b = np[1], c = np[2];
         int4 d = *reinterpret_cast<const int4*>(np + 3);
         if (COUNT) lc.nodes++;
-        // slabs of both children (scene.h BvhNode: centre + half extent; entry / exit = centre -+ half * |1 / d|)
+        // slabs of both children (scene.h BvhNode: centre + half extent, the children's values paired per coordinate;
+        // entry / exit = centre -+ half * |1 / d|)
         const float aix = fabsf(r.inv_d.x), aiy = fabsf(r.inv_d.y), aiz = fabsf(r.inv_d.z);
-        float c0x = (a.x - r.o.x) * r.inv_d.x, c0y = (a.y - r.o.y) * r.inv_d.y, c0z = (a.z - r.o.z) * r.inv_d.z;
-        float n0 = fmaxf(fmaxf(fmaf(-a.w, aix, c0x), fmaf(-b.x, aiy, c0y)), fmaxf(fmaf(-b.y, aiz, c0z), tmin));
-        float f0 = fminf(fminf(fmaf(a.w, aix, c0x), fmaf(b.x, aiy, c0y)), fminf(fmaf(b.y, aiz, c0z), tmax));
-        float c1x = (b.z - r.o.x) * r.inv_d.x, c1y = (b.w - r.o.y) * r.inv_d.y, c1z = (c.x - r.o.z) * r.inv_d.z;
-        float n1 = fmaxf(fmaxf(fmaf(-c.y, aix, c1x), fmaf(-c.z, aiy, c1y)), fmaxf(fmaf(-c.w, aiz, c1z), tmin));
-        float f1 = fminf(fminf(fmaf(c.y, aix, c1x), fmaf(c.z, aiy, c1y)), fminf(fmaf(c.w, aiz, c1z), tmax));
+        float c0x = (a.x - r.o.x) * r.inv_d.x, c0y = (a.z - r.o.y) * r.inv_d.y, c0z = (b.x - r.o.z) * r.inv_d.z;
+        float n0 = fmaxf(fmaxf(fmaf(-b.z, aix, c0x), fmaf(-c.x, aiy, c0y)), fmaxf(fmaf(-c.z, aiz, c0z), tmin));
+        float f0 = fminf(fminf(fmaf(b.z, aix, c0x), fmaf(c.x, aiy, c0y)), fminf(fmaf(c.z, aiz, c0z), tmax));
+        float c1x = (a.y - r.o.x) * r.inv_d.x, c1y = (a.w - r.o.y) * r.inv_d.y, c1z = (b.y - r.o.z) * r.inv_d.z;
+        float n1 = fmaxf(fmaxf(fmaf(-b.w, aix, c1x), fmaf(-c.y, aiy, c1y)), fmaxf(fmaf(-c.w, aiz, c1z), tmin));
+        float f1 = fminf(fminf(fmaf(b.w, aix, c1x), fmaf(c.y, aiy, c1y)), fminf(fmaf(c.w, aiz, c1z), tmax));
         // a few ulp of slack keeps the f32 slab test conservative (Ize 2013)
         bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
         if (h0 && d.x < 0) {
@@ -225,59 +226,136 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
 // ---- resumable traversal (OW render / trace kernel) --------------------------------------------------------------
 constexpr int TRAV_END = (int)0x80000000;
 
-// Per-lane traversal stack: the first SM entries live in shared memory as [entry][thread] (bank = thread, so every
-// push / pop of a warp is ONE conflict-free wavefront whatever the lanes' depths are), deeper entries spill to a local
-// array.  ncu on the all-local stack of round 1: 803 M LDL / STL requests per cover-scene launch, each up to 32
-// wavefronts when the lanes' depths differ, and the pop was the top stall line.
-template <int SM, int THREADS>
+// Per-lane traversal stack.  The first STACK_SM entries live in shared memory as [entry][thread] (bank = thread: every
+// push / pop of a warp is ONE conflict-free wavefront whatever the lanes' depths are); deeper entries spill to a local
+// array that only the rare deep path touches.  The stack pointer `top` is a plain register holding the ADDRESS of the
+// next free shared-memory entry (so push / pop are one predicated STS / LDS and one add, no index arithmetic) while the
+// depth is <= STACK_SM; `deep` counts the entries beyond that.
+// History (ncu, cover scene): round 1's all-local stack cost 803 M LDL / STL requests per launch and the pop was the top
+// stall line; a struct {sp, spill[]} version had ptxas put sp itself into local memory; three divergent paths for push /
+// single / pop were 21 % of ALL warp instructions at ~5 of 32 lanes (profiles/r02_ncu_v5_c4_struct_stack.json).
+constexpr int STACK_SM = 8;
 struct TravStack {
-    int* sm;  // this thread's column: sm[entry * THREADS]
-    int loc[BVH_STACK - SM];
-    int sp;
-    __device__ __forceinline__ void init(int* base, int tid) { sm = base + tid; sp = 0; }
-    __device__ __forceinline__ bool push(int v) {
-        if (sp < SM) sm[sp * THREADS] = v;
-        else if (sp < BVH_STACK) loc[sp - SM] = v;
-        else return false;
-        sp++;
-        return true;
-    }
-    __device__ __forceinline__ int pop() {  // TRAV_END when empty
-        if (sp == 0) return TRAV_END;
-        sp--;
-        return sp < SM ? sm[sp * THREADS] : loc[sp - SM];
-    }
+    unsigned top;   // shared-space ADDRESS of the next free entry of this thread's column; beyond `base + STACK_SM rows` it
+                    // keeps counting in the same units and the entries live in the spill array
+    unsigned base;  // shared-space address of the column (entry e at base + e * THREADS * 4)
 };
+struct StackSpill {
+    int loc[BVH_STACK - STACK_SM];
+};
+template <int THREADS>
+__device__ __forceinline__ void stack_init(TravStack& st, const int* column) {
+    st.base = (unsigned)__cvta_generic_to_shared(column);
+    asm volatile("" : "+r"(st.base));  // opaque: otherwise ptxas re-derives it from %tid in every node step (6 instructions)
+    st.top = st.base;
+}
+__device__ __forceinline__ void stack_reset(TravStack& st) { st.top = st.base; }
+// predicated shared-memory accesses, pinned with inline PTX (left to itself ptxas re-derived the column address from
+// %tid in every node step and branched around the store)
+__device__ __forceinline__ void sts_if(unsigned addr, int v, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.b32 [%0], %1; }" ::"r"(addr), "r"(v), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ int lds_if(unsigned addr, bool p, int otherwise) {
+    int r;
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; mov.b32 %0, %3; @q ld.shared.b32 %0, [%1]; }"
+                 : "=r"(r) : "r"(addr), "r"((int)p), "r"(otherwise) : "memory");
+    return r;
+}
+
+// approximate reciprocal (one MUFU.RCP): the slab test is conservative by construction (slack()), and one ulp on 1 / d
+// scales entry and exit of an axis together
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float3 safe_inv_fast(float3 d) {
+    return f3(fast_rcp(fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x),
+              fast_rcp(fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y),
+              fast_rcp(fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z));
+}
+
+// pop (after a leaf test, or from the rare deep path of a node step); TRAV_END when the stack is empty
+template <int THREADS>
+__device__ __forceinline__ int stack_pop(TravStack& st, const StackSpill& spill) {
+    constexpr unsigned ROW = THREADS * 4u, LIMIT = STACK_SM * ROW;
+    if (st.top == st.base) return TRAV_END;
+    st.top -= ROW;
+    const unsigned off = st.top - st.base;
+    if (off >= LIMIT) return spill.loc[(off - LIMIT) / ROW];
+    return lds_if(st.top, true, TRAV_END);
+}
+template <int THREADS>
+__device__ __forceinline__ bool stack_push_deep(TravStack& st, StackSpill& spill, int v) {  // top is at or beyond the column's end
+    constexpr unsigned ROW = THREADS * 4u, LIMIT = STACK_SM * ROW;
+    const unsigned e = (st.top - st.base - LIMIT) / ROW;
+    if (e >= (unsigned)(BVH_STACK - STACK_SM)) return false;
+    spill.loc[e] = v;
+    st.top += ROW;
+    return true;
+}
+
+// packed dual FP32 FMA (sm_100 FFMA2): (a.x, a.y) * s + (c.x, c.y) and (a.x, a.y) * s + t with scalar s, t
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    ra = *reinterpret_cast<unsigned long long*>(&a);
+    rb = *reinterpret_cast<unsigned long long*>(&b);
+    rc = *reinterpret_cast<unsigned long long*>(&c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float s, float2 c) { return ffma2(a, make_float2(s, s), c); }
+__device__ __forceinline__ float2 ffma2(float2 a, float s, float t) { return ffma2(a, make_float2(s, s), make_float2(t, t)); }
 
 // ONE node step of a lane standing at inner node `node`: slab-test both children, step into the nearer hit child and
-// push the other one, or pop.  Boxes are stored as centre + half extent (scene.h), so entry / exit per axis are
-// fma(-+half, |1/d|, fma(centre, 1/d, -o/d)): three FMAs per axis and child and NO per-axis min / max — round 1's
-// lo / hi form spent 20 FMNMX per step on the ALU pipe (61 % busy, the limiter) against 12 FFMA.  A popped node is not
-// culled against the current hit: its children fail their own slab tests.
-template <bool COUNT, class Stack>
-__device__ __forceinline__ void bvh2_step(const BvhNode* __restrict__ nodes, int& node, Stack& st, const float3 inv_d,
-                                          const float3 oi, const float tmin, const float tmax, LocalCount<COUNT>& lc) {
+// push the other one, or pop.
+//  * Boxes are stored as centre + half extent (scene.h), so entry / exit per axis are fma(-+half, |1/d|, fma(centre, 1/d,
+//    -o/d)): three FMAs per axis and child and NO per-axis min / max — round 1's lo / hi form spent 20 FMNMX per step on
+//    the ALU pipe (61 % busy, the limiter) against 12 FFMA.  The two children's values sit in aligned register pairs,
+//    so each of those FMAs is ONE FFMA2 for both children: 10 FFMA2 + 8 FMNMX(3) per step, where round 1 had 14 + 20.
+//  * The push / pop tail has no divergent paths in the common case: selects, one predicated shared-memory store or load
+//    and one predicated pointer add.  Only a lane whose stack is STACK_SM deep takes the generic path.
+//  * A popped node is not culled against the current hit: its children fail their own slab tests.
+template <bool COUNT, int THREADS>
+__device__ __forceinline__ void bvh2_step(const BvhNode* __restrict__ nodes, int& node, TravStack& st, StackSpill& spill,
+                                          const float3 inv_d, const float3 oi, const float tmin, const float tmax,
+                                          LocalCount<COUNT>& lc) {
     const float4* np = reinterpret_cast<const float4*>(nodes + node);
     const float4 a = np[0], b = np[1], c = np[2];
     const int2 d = *reinterpret_cast<const int2*>(np + 3);
     if (COUNT) lc.nodes++;
+    // both children per instruction: (c0, c1) pairs x scalar 1/d (FFMA2 broadcasts a scalar operand)
+    const float2 tcx = ffma2(make_float2(a.x, a.y), inv_d.x, -oi.x);
+    const float2 tcy = ffma2(make_float2(a.z, a.w), inv_d.y, -oi.y);
+    const float2 tcz = ffma2(make_float2(b.x, b.y), inv_d.z, -oi.z);
+    const float2 hx = make_float2(b.z, b.w), hy = make_float2(c.x, c.y), hz = make_float2(c.z, c.w);
     const float aix = fabsf(inv_d.x), aiy = fabsf(inv_d.y), aiz = fabsf(inv_d.z);
-    const float c0x = fmaf(a.x, inv_d.x, -oi.x), c0y = fmaf(a.y, inv_d.y, -oi.y), c0z = fmaf(a.z, inv_d.z, -oi.z);
-    const float n0 = fmaxf(fmaxf(fmaf(-a.w, aix, c0x), fmaf(-b.x, aiy, c0y)), fmaxf(fmaf(-b.y, aiz, c0z), tmin));
-    const float f0 = fminf(fminf(fmaf(a.w, aix, c0x), fmaf(b.x, aiy, c0y)), fminf(fmaf(b.y, aiz, c0z), tmax));
-    const float c1x = fmaf(b.z, inv_d.x, -oi.x), c1y = fmaf(b.w, inv_d.y, -oi.y), c1z = fmaf(c.x, inv_d.z, -oi.z);
-    const float n1 = fmaxf(fmaxf(fmaf(-c.y, aix, c1x), fmaf(-c.z, aiy, c1y)), fmaxf(fmaf(-c.w, aiz, c1z), tmin));
-    const float f1 = fminf(fminf(fmaf(c.y, aix, c1x), fmaf(c.z, aiy, c1y)), fminf(fmaf(c.w, aiz, c1z), tmax));
-    const bool h0 = n0 <= slack(f0), h1 = n1 <= slack(f1);
-    if (h0 && h1) {
-        const bool swap = n1 < n0;
-        if (!st.push(swap ? d.x : d.y)) lc.overflow++;
-        node = swap ? d.y : d.x;
-    } else if (h0 || h1) {
-        node = h0 ? d.x : d.y;
-    } else {
-        node = st.pop();
+    const float2 nx = ffma2(hx, -aix, tcx), ny = ffma2(hy, -aiy, tcy), nz = ffma2(hz, -aiz, tcz);
+    const float2 fx = ffma2(hx, aix, tcx), fy = ffma2(hy, aiy, tcy), fz = ffma2(hz, aiz, tcz);
+    const float n0 = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, tmin)), n1 = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, tmin));
+    const float2 f = make_float2(fminf(fminf(fx.x, fy.x), fminf(fz.x, tmax)), fminf(fminf(fx.y, fy.y), fminf(fz.y, tmax)));
+    const float2 fs = ffma2(make_float2(fabsf(f.x), fabsf(f.y)), 5e-7f, f);  // slack() of both
+    const bool h0 = n0 <= fs.x, h1 = n1 <= fs.y;
+    const bool both = h0 && h1, any = h0 || h1;
+    const bool second_first = h1 && (!h0 || n1 < n0);
+    const int nearc = second_first ? d.y : d.x;
+    const int farc = second_first ? d.x : d.y;
+    constexpr unsigned ROW = THREADS * 4u, LIMIT = STACK_SM * ROW;
+    if (st.top - st.base >= LIMIT) {  // rare: the column is full, the spill rows are involved
+        if (both) {
+            if (!stack_push_deep<THREADS>(st, spill, farc)) lc.overflow++;
+            node = nearc;
+        } else {
+            node = any ? nearc : stack_pop<THREADS>(st, spill);
+        }
+        return;
     }
+    sts_if(st.top, farc, both);
+    st.top += both ? ROW : 0u;
+    const bool popping = !any && st.top != st.base;
+    st.top -= popping ? ROW : 0u;
+    const int popped = lds_if(st.top, popping, TRAV_END);
+    node = any ? nearc : popped;
 }
 
 // ---- work distribution ----------------------------------------------------------------------------------

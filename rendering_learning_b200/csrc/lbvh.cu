@@ -350,9 +350,9 @@ __global__ void k_pack(const float* __restrict__ aabb, const int* __restrict__ s
             float c[3], h[3];
             centre_half(aabb, c, h);
             BvhNode nd;
-            nd.a = make_float4(c[0], c[1], c[2], h[0]);
-            nd.b = make_float4(h[1], h[2], 0.0f, 0.0f);
-            nd.c = make_float4(0.0f, -1.0f, -1.0f, -1.0f);  // empty second slot: entry > exit for every ray
+            nd.a = make_float4(c[0], 0.0f, c[1], 0.0f);
+            nd.b = make_float4(c[2], 0.0f, h[0], -1.0f);  // empty second slot (half = -1): entry > exit for every ray
+            nd.c = make_float4(h[1], -1.0f, h[2], -1.0f);
             nd.d = make_int4(~prim_ref[0], ~prim_ref[0], 0, 0);
             nodes[0] = nd;
         }
@@ -375,9 +375,9 @@ __global__ void k_pack(const float* __restrict__ aabb, const int* __restrict__ s
         centre_half(src, cc[c], hh[c]);
     }
     BvhNode nd;
-    nd.a = make_float4(cc[0][0], cc[0][1], cc[0][2], hh[0][0]);
-    nd.b = make_float4(hh[0][1], hh[0][2], cc[1][0], cc[1][1]);
-    nd.c = make_float4(cc[1][2], hh[1][0], hh[1][1], hh[1][2]);
+    nd.a = make_float4(cc[0][0], cc[1][0], cc[0][1], cc[1][1]);
+    nd.b = make_float4(cc[0][2], cc[1][2], hh[0][0], hh[1][0]);
+    nd.c = make_float4(hh[0][1], hh[1][1], hh[0][2], hh[1][2]);
     nd.d = make_int4(id[0], id[1], 0, 0);
     nodes[i] = nd;
 }

@@ -166,7 +166,11 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             // a huge sphere seen from near its surface (the r = 1000 ground of the cover scene): r^2 - |perp|^2
             // cancels ~7 digits, more than f32 has.  One such primitive sits near the BVH root, so its
             // quadratic is evaluated in f64 (B200 runs FP64 at half the FP32 rate; the cost is one test per ray).
-            double ox = (double)oc.x, oy = (double)oc.y, oz = (double)oc.z;
+            // o - centre in f64 as well: in f32 the ray's height above an r = 1000 sphere keeps 6e-5 of absolute precision,
+            // which a grazing ray turns into 4e-4 of relative error in t (measured on the reference's scattered rays)
+            double ox = (double)o.x - fma((double)dc.x, (double)time, (double)c.x);
+            double oy = (double)o.y - fma((double)dc.y, (double)time, (double)c.y);
+            double oz = (double)o.z - fma((double)dc.z, (double)time, (double)c.z);
             double dx = (double)d.x, dy = (double)d.y, dz = (double)d.z;
             double a = dx * dx + dy * dy + dz * dz;
             double hbd = ox * dx + oy * dy + oz * dz;
@@ -499,8 +503,10 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     p.depth = 0;
     // traversal (resumable)
     int node = TRAV_END;
-    TravStack<0, 256> st;  // all-local stack: the round-1 baseline the v6 kernel is measured against
-    st.init(nullptr, 0);
+    __shared__ int sm_stack[STACK_SM * 256];  // [entry][thread]: the first STACK_SM entries of every lane's traversal stack
+    TravStack st;
+    stack_init<256>(st, sm_stack + threadIdx.x);
+    StackSpill spill;
     float3 inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
     float tmin = 0.0f;
     TriShear shear;
@@ -510,12 +516,14 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
     // queue (warp-uniform, one slot per warp in shared memory): the current reserved batch [next, end) and the base of
     // the prefetched next batch, whose atomic was issued one batch ago
-    __shared__ long long sm_qnext[8], sm_qend[8];
+    __shared__ long long sm_qnext[8], sm_qend[8], sm_qfirst[8];
     __shared__ unsigned long long sm_qbase[8];
     __shared__ int sm_qdry[8], sm_qsize[8];
+    constexpr int OW_ITEM_TABLE = 64;  // >= the largest batch a warp reserves (launch_ow_render clamps qbatch to 64)
+    __shared__ int sm_it_xy[8][OW_ITEM_TABLE], sm_it_chunk[8][OW_ITEM_TABLE], sm_it_s0[8][OW_ITEM_TABLE], sm_it_s1[8][OW_ITEM_TABLE];
     const int wid = threadIdx.x >> 5;
     if (lane == 0) {
-        sm_qnext[wid] = sm_qend[wid] = 0;
+        sm_qnext[wid] = sm_qend[wid] = sm_qfirst[wid] = 0;
         sm_qdry[wid] = 0;
         sm_qsize[wid] = qbatch;
         sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
@@ -570,30 +578,53 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                     sm_qsize[wid] = want;
                     sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)want)
                                               : atomicAdd(queue, (unsigned long long)want);
+                    sm_qfirst[wid] = cur_next;
                 }
+                // Decode the WHOLE batch now, with every lane: item -> (job, chunk, pixel, sample range) is ~300 instructions of
+                // 64-bit divisions and a binary search, and round 1 ran it per item at ~2 of 32 lanes — whenever a service
+                // round happened to include a lane that had just finished its item — for 8 % of all warp instructions
+                // (profiles/r02_ncu_v5_c4_struct_stack.json: svc_queue + kernels.h + tile_pixel lines).
+                for (int k = (int)lane; k < OW_ITEM_TABLE; k += 32) {
+                    const long long item = cur_next + k;
+                    int xy = -1, chunk = 0, s0 = 0, s1 = 0;
+                    if (item < cur_end) {
+                        const int j = find_job(jt, item);
+                        const rl_job job = jt_job(jt, j);
+                        const long long local = item - jt_prefix(jt, j);
+                        const int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
+                        const long long pp = padded_pixels(w, hgt);
+                        const int ck = (int)(local / pp);
+                        int px, py;
+                        tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
+                        if (px < w && py < hgt) {
+                            chunk = job.chunk_begin + ck;
+                            ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s0, &s1);
+                            if (cam.max_depth <= 0) s0 = s1;  // depth 0: every sample is black (camera.rs:239-241)
+                            xy = ((job.y0 + py) << 16) | (job.x0 + px);
+                        }
+                    }
+                    sm_it_xy[wid][k] = xy;
+                    sm_it_chunk[wid][k] = chunk;
+                    sm_it_s0[wid][k] = s0;
+                    sm_it_s1[wid][k] = s1;
+                }
+                __syncwarp();
             }
             long long avail = cur_end - cur_next;
             int rank_in = __popc(mask & ((1u << lane) - 1u));
             if (need) {
                 if (rank_in < avail) {
-                    long long item = cur_next + rank_in;
-                    int j = find_job(jt, item);
-                    rl_job job = jt_job(jt, j);
-                    long long local = item - jt_prefix(jt, j);
-                    int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
-                    long long pp = padded_pixels(w, hgt);
-                    int ck = (int)(local / pp);
-                    int px, py;
-                    tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
-                    if (px < w && py < hgt) {  // padded slots outside the rectangle are simply skipped
-                        int x = job.x0 + px, y = job.y0 + py, chunk = job.chunk_begin + ck, s_end;
-                        ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
-                        if (cam.max_depth <= 0) s = s_end;  // depth 0: every sample is black (camera.rs:239-241)
+                    // the batch was decoded when it was installed (all 32 lanes, two items each): three shared-memory reads
+                    const int k = (int)(cur_next + rank_in - sm_qfirst[wid]);
+                    const int xy = sm_it_xy[wid][k];
+                    if (xy >= 0) {  // padded slots outside the rectangle are simply skipped
+                        const int x = xy & 0xffff, y = xy >> 16;
+                        s = sm_it_s0[wid][k];
                         pixel = (unsigned)(y * cam.width + x);
                         sm_x[tid] = x;
                         sm_y[tid] = y;
-                        sm_chunk[tid] = chunk;
-                        sm_send[tid] = s_end;
+                        sm_chunk[tid] = sm_it_chunk[wid][k];
+                        sm_send[tid] = sm_it_s1[wid][k];
                         sm_acc[0][tid] = sm_acc[1][tid] = sm_acc[2][tid] = 0.0f;
                         has_item = true;
                     }
@@ -619,14 +650,14 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             // unit direction: t is internal to this kernel (hit point = o + d t either way), and with |d| = 1 the
             // sphere quadratic, the medium's ray length and the tmin scale lose their divisions by d.d
             p.d = p.d * rsqrtf(dot(p.d, p.d));
-            inv_d = safe_inv(p.d);
+            inv_d = safe_inv_fast(p.d);
             oi = p.o * inv_d;
             tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // ow_tmin with |d| = 1
             if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
             if (PRIMS & PRIMS_MEDIA)
                 ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
-            st.sp = 0;
+            stack_reset(st);
             if (COUNT) lc.rays++;
             for (int k = 0; k < sc.n_big; k++)  // the big list: once per ray, here, with the serviced lanes
                 ow_leaf_test_od<COUNT, PRIMS>(sc, sc.big_refs[k], p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc, ray_rnd);
@@ -640,7 +671,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             // leaf round: every lane parked at a leaf tests it and pops
             if (node < 0 && node != TRAV_END) {
                 ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, p.o, p.d, shear, p.time, p.self_ref, tmin, hit, lc, ray_rnd);
-                node = st.pop();
+                node = stack_pop<256>(st, spill);
             }
             const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));
             if (n_end == 32 || n_end - n_done >= svc_min) break;
@@ -652,7 +683,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 // 4 -> 12.63 / 65.4: two halve the ballots while a lane that parks after the first step idles one step only)
 #pragma unroll
                 for (int k = 0; k < (OPT < 1 ? 1 : OPT); k++) {
-                    if (node >= 0) bvh2_step<COUNT>(sc.nodes, node, st, inv_d, oi, tmin, hit.t, lc);
+                    if (node >= 0) bvh2_step<COUNT, 256>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc);
                 }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);
@@ -680,7 +711,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
 // MODE_TRACE runs caller-supplied rays through the SAME queues, refill, big-list start, node steps and leaf rounds and
 // writes rl_hit records: rl_trace_batch is the production traversal, not a second implementation.
 namespace v6 {
-constexpr int THREADS = 256, QCAP = 512, STACK_SM = 8, EMPTY = -1;
+constexpr int THREADS = 256, QCAP = 512, EMPTY = -1;
 constexpr int MODE_RENDER = 0, MODE_TRACE = 1;
 // slot words
 enum { OX, OY, OZ, DX, DY, DZ, TIME, SELF, HT, HREF, THRX, THRY, THRZ, DEPTH, XY, S, SEND, CHUNK, ACCX, ACCY, ACCZ, FLAGS, N_BASE };
@@ -838,8 +869,9 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
 
     // ---- lane state: the ray this lane is traversing ----
     int slot = -1, node = TRAV_END;
-    TravStack<STACK_SM, THREADS> st;
-    st.init(stack_base, tid);
+    TravStack st;
+    stack_init<THREADS>(st, stack_base + tid);
+    StackSpill spill;
     float3 o = f3(0.0f, 0.0f, 0.0f), d = f3(0.0f, 0.0f, 1.0f), inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
     float tmin = 0.0f, time = 0.0f;
     int self_ref = -1;
@@ -884,11 +916,11 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
                     hit.b2 = SL(HB2, got);
                 }
                 if (PRIMS & PRIMS_MEDIA) ray_rnd = (unsigned)SLI(RND, got);
-                inv_d = safe_inv(d);
+                inv_d = safe_inv_fast(d);
                 oi = o * inv_d;
                 tmin = fmaf(1e-5f, max_abs(o), 1e-6f);  // ow_tmin with |d| = 1
                 if (PRIMS & PRIMS_TRIS) shear = make_shear(o, d);
-                st.sp = 0;
+                stack_reset(st);
                 node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
             }
         }
@@ -1089,7 +1121,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
         while (true) {
             if (node < 0 && node != TRAV_END) {  // leaf round: every lane parked at a leaf tests it and pops
                 ow_leaf_test_od<COUNT, PRIMS>(sc, ~node, o, d, shear, time, self_ref, tmin, hit, lc, ray_rnd);
-                node = st.pop();
+                node = stack_pop<THREADS>(st, spill);
             }
             const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));  // idle lanes count as ended
             if (n_end == 32 || n_end - n_idle0 >= exit_min) break;
@@ -1100,7 +1132,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
             do {
 #pragma unroll
                 for (int k = 0; k < 2; k++) {  // two steps per ballot (measured in round 1: 1 / 2 / 3 / 4 -> 12.44 / 12.11 / 12.39 / 12.63 ms)
-                    if (node >= 0) bvh2_step<COUNT>(sc.nodes, node, st, inv_d, oi, tmin, hit.t, lc);
+                    if (node >= 0) bvh2_step<COUNT, THREADS>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc);
                 }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);

@@ -93,14 +93,16 @@ struct DevLight {
     float4 pos, intensity;
 };
 
-// BVH2 traversal node: both children's boxes live in the parent, as CENTRE + HALF EXTENT. 64 B = 4 x LDG.128.
-// The slab test is then centre * (1/d) - o/d -+ half * |1/d| per axis: FMAs only, no per-axis min / max (device.cuh
-// bvh2_step).  lbvh.cu k_pack rounds the half extent UP so that [centre - half, centre + half] contains the f32 box the
-// hierarchy was refitted with; an empty child slot has half = -1 (entry > exit for every ray).
+// BVH2 traversal node: both children's boxes live in the parent, as CENTRE + HALF EXTENT, the two children's values of
+// each coordinate ADJACENT (an aligned register pair after the LDG.128). 64 B = 4 x LDG.128.
+// The slab test is then centre * (1/d) - o/d -+ half * |1/d| per axis: FMAs only, no per-axis min / max, and each FMA is
+// ONE packed FFMA2 (fma.rn.f32x2, new on sm_100) that serves both children (device.cuh bvh2_step).  lbvh.cu k_pack
+// rounds the half extent UP so that [centre - half, centre + half] contains the f32 box the hierarchy was refitted with;
+// an empty child slot has half = -1 (entry > exit for every ray).
 struct BvhNode {
-    float4 a;  // c0.centre.x c0.centre.y c0.centre.z c0.half.x
-    float4 b;  // c0.half.y c0.half.z c1.centre.x c1.centre.y
-    float4 c;  // c1.centre.z c1.half.x c1.half.y c1.half.z
+    float4 a;  // c0.centre.x c1.centre.x c0.centre.y c1.centre.y
+    float4 b;  // c0.centre.z c1.centre.z c0.half.x   c1.half.x
+    float4 c;  // c0.half.y   c1.half.y   c0.half.z   c1.half.z
     int4 d;    // child0, child1 (>=0 internal node, <0 = ~leaf ref), 0, 0
 };
 

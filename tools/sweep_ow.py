@@ -53,9 +53,10 @@ def run(name, world, params, grid, reps=3):
 
 v5 = [{"ow.variant": 5}]
 if mode == "quick":
-    g6 = [{}, {"ow.minb": 3}, {"ow.minb": 4}, {"ow.slots": 256}, {"ow.slots": 320}, {"ow.slots": 512}, {"ow.exit_min": 4}, {"ow.exit_min": 12},
-          {"ow.exit_min": 16}, {"ow.svc_lo": 8}, {"ow.svc_lo": 24}, {"ow.leaf_min": 4}, {"ow.leaf_min": 12}, {"ow.leaf_min": 16},
-          {"ow.minb": 3, "ow.slots": 512}, {"ow.minb": 3, "ow.slots": 320}, {"ow.ctas_per_sm": 3}, {"ow.ctas_per_sm": 2}]
+    g6 = [{}, {"ow.minb": 3}, {"ow.exit_min": 16}, {"ow.exit_min": 16, "ow.minb": 3}, {"ow.exit_min": 24, "ow.minb": 3}]
+    g5 = [{"ow.variant": 5, "ow.svc_min": a, "ow.leaf_min": b} for a in (16, 20, 24) for b in (6, 8, 12)]
+    g5 += [{"ow.variant": 5, "ow.minb": 3}, {"ow.variant": 5, "ow.minb": 4}]
+    g6 = g5 + g6
 else:
     g6 = [dict(zip(("ow.minb", "ow.slots", "ow.exit_min", "ow.svc_lo", "ow.leaf_min"), v))
           for v in itertools.product((3, 4), (256, 320, 384, 512), (6, 8, 12), (8, 16, 24), (6, 8, 12))]
