@@ -522,7 +522,7 @@ def main():
                                                  "(SURVEY.md §8d); achieved/peak/frac = algorithmic FP32 flops vs the measured FP32 FMA peak",
                 "achieved": ach_tf, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
                 "frac": ach_tf / peaks["fp32_tflops"], "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_ow_render6" if wl["kind"] == "ow" else "k_rtc_render", "kernel_ms": kms,
+                "kernel": "k_ow_render5" if wl["kind"] == "ow" else "k_rtc_render", "kernel_ms": kms,
                 "flops_per_launch": fl, "peak_source": "measured live (rl_measure_peaks: FMA chains, all SMs)",
                 "ncu": prof or None,
                 "l1_algorithmic": {"bytes_per_launch": by, "achieved": by / (kms * 1e-3) / 1e9, "unit": "GB/s",

@@ -34,7 +34,8 @@ __host__ __device__ inline void ow_chunk_range(int spp, int n_chunks, int chunk,
 // Scheduling parameters of the OW render kernel.  0 = the measured default of the scene's instantiation.  They change
 // WHEN work is done, never what is computed: the image is bit-identical for every setting (tests/test_gpu_ow.py).
 struct OwTuning {
-    int variant = 6;      // 6: CTA-pooled paths (production); 5: round 1's per-lane kernel (kept as the A/B baseline)
+    int variant = 5;      // 5: per-lane paths, service rounds inside the warp (production); 6: CTA-pooled paths (the measured
+                          // shared-memory wavefront experiment, 1.6-1.9x slower: DESIGN.md §4)
     int slots = 0;        // v6: path slots per CTA (256 .. 512)
     int minb = 0;         // resident CTAs per SM the kernel is compiled for (3 or 4)
     int ctas_per_sm = 0;  // launch fewer CTAs per SM than fit

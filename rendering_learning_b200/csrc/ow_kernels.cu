@@ -481,10 +481,18 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
 // runs for all parked lanes together once `leaf_min` of them wait (or nobody can step).  leaf_min = 32 degenerates to
 // the while-while schedule (v4).  ncu (profiles/r01_ncu_k_ow_render_v4.json, _v5.json): node steps run at 20 instead of 12.5
 // lanes, the whole kernel at 16 instead of 11.3.
-template <bool COUNT, int MINB, int PRIMS, int OPT = 2>
+// TRACE = true runs caller-supplied rays through the SAME loop (work items = ray indices, "service" = write the rl_hit of
+// the finished ray and load the next one): rl_trace_batch is this kernel, not a second traversal.
+struct TraceIO {
+    const rl_ray* rays;
+    const int* self_refs;  // optional: the leaf ref each ray starts on (-1 none)
+    rl_hit* hits;
+};
+template <bool COUNT, int MINB, int PRIMS, bool TRACE = false, int OPT = 2>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
-                                                          int sys_queue, int qbatch, long long q_guided, int svc_min, int leaf_min) {
+                                                          int sys_queue, int qbatch, long long q_guided, int svc_min, int leaf_min,
+                                                          TraceIO tio) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     const int tid = threadIdx.x;
     bool has_item = false, alive = false, done = false;
     int s = 0;
-    unsigned pixel = 0;
+    unsigned pixel = 0, retired = 0;
     // path
     Path p;
     p.depth = 0;
@@ -533,7 +541,23 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     while (true) {
         // ================= service: every lane that is not mid-traversal =================
         const bool svc = node == TRAV_END && !done;
-        if (svc && alive) {  // its traversal just finished: hit record + emitted + scatter
+        if (TRACE && svc && alive) {  // a traced ray came back: its rl_hit (t in the caller's units: the ray ran with |d| = 1)
+            rl_hit out;
+            out.node = -1;
+            out.t = hit.t * sm_thr[0][tid];
+            out.u = hit.b1;
+            out.v = hit.b2;
+            if (hit.ref >= 0) {
+                const int type = ref_type(hit.ref), idx = ref_index(hit.ref);
+                out.node = type == REF_SPHERE ? sc.sphere_node[idx]
+                         : type == REF_QUAD ? sc.quad_node[idx]
+                         : type == REF_TRI ? __float_as_int(sc.tri_verts[idx].p1.w) : -1;
+            }
+            tio.hits[s] = out;
+            alive = false;
+            has_item = false;
+        }
+        if (!TRACE && svc && alive) {  // its traversal just finished: hit record + emitted + scatter
             unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
             uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
             float3 rad;
@@ -550,12 +574,13 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 sm_thr[2][tid] = p.thr.z;
             }
         }
-        if (svc && has_item && !alive && s == sm_send[tid]) {
+        if (!TRACE && svc && has_item && !alive && s == sm_send[tid]) {
             // ONE 16-byte store per finished item (over NVLink when the buffer is rank 0's: three 4-byte stores per
             // item were 134 M small remote writes per 8-GPU cover-scene step)
             size_t idx = ((size_t)sm_chunk[tid] * cam.height + sm_y[tid]) * cam.width + sm_x[tid];
             reinterpret_cast<float4*>(partial)[idx] = make_float4(sm_acc[0][tid], sm_acc[1][tid], sm_acc[2][tid], 0.0f);
             has_item = false;
+            retired++;
         }
         const bool need = svc && !has_item;
         const unsigned mask = __ballot_sync(FULL, need);
@@ -584,7 +609,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 // 64-bit divisions and a binary search, and round 1 ran it per item at ~2 of 32 lanes — whenever a service
                 // round happened to include a lane that had just finished its item — for 8 % of all warp instructions
                 // (profiles/r02_ncu_v5_c4_struct_stack.json: svc_queue + kernels.h + tile_pixel lines).
-                for (int k = (int)lane; k < OW_ITEM_TABLE; k += 32) {
+                for (int k = (int)lane; !TRACE && k < OW_ITEM_TABLE; k += 32) {
                     const long long item = cur_next + k;
                     int xy = -1, chunk = 0, s0 = 0, s1 = 0;
                     if (item < cur_end) {
@@ -613,7 +638,19 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             long long avail = cur_end - cur_next;
             int rank_in = __popc(mask & ((1u << lane) - 1u));
             if (need) {
-                if (rank_in < avail) {
+                if (TRACE && rank_in < avail) {  // work item = ray index
+                    const long long item = cur_next + rank_in;
+                    const rl_ray r = tio.rays[item];
+                    p.o = f3(r.origin[0], r.origin[1], r.origin[2]);
+                    p.d = f3(r.direction[0], r.direction[1], r.direction[2]);
+                    p.time = r.time;
+                    p.self_ref = tio.self_refs ? tio.self_refs[item] : -1;
+                    p.depth = 1;
+                    sm_thr[0][tid] = rsqrtf(dot(p.d, p.d));  // t(caller) = t(unit direction) / |d|: the same factor normalises d below
+                    s = (int)item;
+                    has_item = true;
+                    alive = true;
+                } else if (rank_in < avail) {
                     // the batch was decoded when it was installed (all 32 lanes, two items each): three shared-memory reads
                     const int k = (int)(cur_next + rank_in - sm_qfirst[wid]);
                     const int xy = sm_it_xy[wid][k];
@@ -627,6 +664,8 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                         sm_send[tid] = sm_it_s1[wid][k];
                         sm_acc[0][tid] = sm_acc[1][tid] = sm_acc[2][tid] = 0.0f;
                         has_item = true;
+                    } else {
+                        retired++;  // nothing to render, but it IS a work item of the job list (rl_ow_job_items counts padded slots)
                     }
                 } else if (q_dry) {
                     done = true;
@@ -641,7 +680,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             }
             __syncwarp();
         }
-        if (svc && has_item && !alive && s < sm_send[tid]) {  // path regeneration
+        if (!TRACE && svc && has_item && !alive && s < sm_send[tid]) {  // path regeneration
             ow_camera_ray(cam, sm_x[tid], sm_y[tid], (unsigned)(cam.first_sample + s), p);
             sm_thr[0][tid] = sm_thr[1][tid] = sm_thr[2][tid] = 1.0f;
             alive = true;
@@ -654,7 +693,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             oi = p.o * inv_d;
             tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // ow_tmin with |d| = 1
             if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
-            if (PRIMS & PRIMS_MEDIA)
+            if ((PRIMS & PRIMS_MEDIA) && !TRACE)
                 ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
             stack_reset(st);
@@ -687,6 +726,15 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);
+        }
+    }
+    // completion accounting: items this GPU finished, added to the counter next to the queue (rank 0's over NVLink when the
+    // queue is shared), so the owner can tell a finished render from one a peer dropped out of
+    if (!TRACE) {
+        for (int off = 16; off > 0; off >>= 1) retired += __shfl_xor_sync(FULL, retired, off);
+        if (lane == 0 && retired) {
+            if (sys_queue) atomicAdd_system(queue + 1, (unsigned long long)retired);
+            else atomicAdd(queue + 1, (unsigned long long)retired);
         }
     }
     lc.flush(counters);
@@ -731,11 +779,7 @@ struct Ctl {
     volatile unsigned long long nx_base;              // prefetched next batch (its atomic was issued one batch ago)
 };
 
-struct TraceIO {
-    const rl_ray* rays;
-    const int* self_refs;  // optional: the leaf ref each ray starts on (-1 none)
-    rl_hit* hits;
-};
+using rl::TraceIO;
 
 __device__ __forceinline__ void ring_push(int* ring, volatile unsigned* tail, unsigned mask, bool pred, int id, unsigned lane) {
     if (!mask) return;
@@ -825,7 +869,7 @@ template <bool COUNT, int MINB, int PRIMS, int MODE>
 __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
                                                           int sys_queue, int qbatch, long long q_guided, int P, int svc_lo,
-                                                          int exit_min, int leaf_min, v6::TraceIO tio) {
+                                                          int exit_min, int leaf_min, TraceIO tio) {
     using namespace v6;
     constexpr bool HAS_B = (PRIMS & (PRIMS_TRIS | PRIMS_QUADS | PRIMS_MEDIA)) != 0;
     constexpr int NW = slot_words(PRIMS);
@@ -1258,9 +1302,9 @@ static OwCam make_cam(const rl_ow_camera* p, uint32_t first_sample) {
 
 namespace {
 constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
-typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int);
+typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int, TraceIO);
 typedef void (*K6)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int, int, int,
-                   v6::TraceIO);
+                   TraceIO);
 
 // which instantiation a scene runs: spheres only / no spheres / every surface / everything (media, Noise)
 int scene_prims(const DevScene& sc) {
@@ -1284,23 +1328,51 @@ K6 pick_k6(int prims, int minb, bool instrumented) {
 #undef RL_K6
 }
 
+template <bool TRACE>
 K5 pick_k5(int prims, int minb, bool instrumented) {
-#define RL_K5(P_)                                                                                       \
-    (minb >= 4 ? (instrumented ? (K5)k_ow_render5<true, 4, P_> : (K5)k_ow_render5<false, 4, P_>)       \
-               : (instrumented ? (K5)k_ow_render5<true, 3, P_> : (K5)k_ow_render5<false, 3, P_>))
+#define RL_K5(P_)                                                                                                     \
+    (minb >= 4 ? (instrumented ? (K5)k_ow_render5<true, 4, P_, TRACE> : (K5)k_ow_render5<false, 4, P_, TRACE>)       \
+               : (instrumented ? (K5)k_ow_render5<true, 3, P_, TRACE> : (K5)k_ow_render5<false, 3, P_, TRACE>))
     switch (prims) {
         case PRIMS_SPHERES: return RL_K5(PRIMS_SPHERES);
         case PRIMS_FLAT: return RL_K5(PRIMS_FLAT);
         case PRIMS_ALL: return RL_K5(PRIMS_ALL);
-        default: return instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FULL> : (K5)k_ow_render5<false, 3, PRIMS_FULL>;
+        default: return instrumented ? (K5)k_ow_render5<true, 3, PRIMS_FULL, TRACE> : (K5)k_ow_render5<false, 3, PRIMS_FULL, TRACE>;
     }
 #undef RL_K5
+}
+
+// one launch of the production kernel (render or trace): occupancy, grid, batch sizes, thresholds
+cudaError_t launch_k5(K5 k5, int prims, const DevScene& sc, const OwCam& c, const JobTable& jt, float* d_partial,
+                      unsigned long long* d_queue, Counters* d_counters, int sm_count, cudaStream_t stream, bool shared_queue,
+                      const OwTuning& tune, const TraceIO& tio) {
+    // service threshold: sphere scenes shade cheaply and prefer fuller service rounds; parked lanes per leaf round
+    // (gpurun_out sweeps of round 2, cover scene / Cornell box + spot: 24 / 8 -> 96.3 ms, 20 / 8 -> 55.9 ms)
+    const int svc_min = tune.svc_min > 0 ? tune.svc_min : (prims == PRIMS_SPHERES ? 24 : 20);
+    const int leaf_min = tune.leaf_min > 0 ? tune.leaf_min : 8;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
+    long long want = (jt.n_items + 255) / 256;
+    long long grid = (long long)sm_count * per_sm;  // persistent: every SM full, a multiple of the SM count
+    if (grid > want && !shared_queue) grid = want;
+    if (grid < 1) grid = 1;
+    // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
+    long long per_warp = jt.n_items / (grid * 8 * 4);
+    int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
+    // below this many remaining items a warp reserves 32 instead of qbatch (a shared queue feeds up to 8 GPUs)
+    const long long q_guided = grid * 8 * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
+    k5<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, shared_queue ? 1 : 0, qbatch, q_guided, svc_min,
+                                           leaf_min, tio);
+    return cudaGetLastError();
 }
 
 // one v6 launch (render or trace): shared-memory size, occupancy, grid, batch sizes
 cudaError_t launch_k6(K6 k, int prims, const DevScene& sc, const OwCam& c, const JobTable& jt, float* d_partial,
                       unsigned long long* d_queue, Counters* d_counters, int sm_count, cudaStream_t stream, bool shared_queue,
-                      const OwTuning& tune, const v6::TraceIO& tio) {
+                      const OwTuning& tune, const TraceIO& tio) {
     int P = tune.slots > 0 ? tune.slots : 384;
     P = (P + 31) / 32 * 32;
     if (P < 256) P = 256;  // at least one slot per lane, or lanes starve by construction
@@ -1343,29 +1415,12 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
     // resident CTAs per SM the kernel is compiled for (register budget): the spheres-only and no-spheres builds fit 64
     // registers (4 CTAs/SM); the builds that carry every primitive kind are better at 80 (3 CTAs/SM)
     const int minb = tune.minb ? tune.minb : ((prims == PRIMS_SPHERES || prims == PRIMS_FLAT) ? 4 : 3);
-    if (tune.variant != 5) {
-        v6::TraceIO tio{nullptr, nullptr, nullptr};
+    TraceIO tio{nullptr, nullptr, nullptr};
+    if (tune.variant == 6)  // the pooled-paths experiment (measured 1.6-1.9x SLOWER; kept selectable for the A/B)
         return launch_k6(pick_k6<v6::MODE_RENDER>(prims, minb, instrumented), prims, sc, c, jt, d_partial, d_queue, d_counters,
                          sm_count, stream, shared_queue, tune, tio);
-    }
-    // v5 (round 1's kernel: per-lane paths, threshold-triggered service inside the warp), kept as the measured A/B baseline
-    K5 k5 = pick_k5(prims, minb, instrumented);
-    const int svc_min = tune.svc_min > 0 ? tune.svc_min : (prims == PRIMS_SPHERES ? 24 : 16);
-    const int leaf_min = tune.leaf_min > 0 ? tune.leaf_min : (prims == PRIMS_SPHERES ? 8 : 12);
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5, 256, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    long long want = (jt.n_items + 255) / 256;
-    long long grid = (long long)sm_count * per_sm;
-    if (grid > want && !shared_queue) grid = want;
-    if (grid < 1) grid = 1;
-    long long per_warp = jt.n_items / (grid * 8 * 4);
-    int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
-    const long long q_guided = grid * 8 * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
-    k5<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, shared_queue ? 1 : 0, qbatch, q_guided, svc_min,
-                                           leaf_min);
-    return cudaGetLastError();
+    return launch_k5(pick_k5<false>(prims, minb, instrumented), prims, sc, c, jt, d_partial, d_queue, d_counters, sm_count, stream,
+                     shared_queue, tune, tio);
 }
 
 cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream) {
@@ -1387,8 +1442,9 @@ cudaError_t launch_encode_ow_u8(const float* d_rgb_sum, uint8_t* d_out, size_t n
     return cudaGetLastError();
 }
 
-// rl_trace_batch for OW scenes: the rays run through the render kernel's own queues, big-list start, node steps and leaf
-// rounds (k_ow_render6 in MODE_TRACE).  d_self_refs (optional) = the leaf ref each ray starts on.
+// rl_trace_batch for OW scenes: the rays run through the RENDER kernel itself (TRACE instantiation of the variant the
+// ctx renders with): same work queue, service / refill rounds, unit directions, t_min rule, start-on-surface rule, big
+// list at ray start, node steps and leaf rounds.  d_self_refs (optional) = the leaf ref each ray starts on.
 cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, const int* d_self_refs, uint64_t n, rl_hit* d_hits,
                             unsigned long long* d_queue, Counters* d_counters, bool instrumented, int sm_count,
                             cudaStream_t stream, const OwTuning& tune) {
@@ -1403,9 +1459,12 @@ cudaError_t launch_ow_trace(const DevScene& sc, const rl_ray* d_rays, const int*
     jt.n_items = (long long)n;
     const int prims = scene_prims(sc);
     const int minb = tune.minb ? tune.minb : ((prims == PRIMS_SPHERES || prims == PRIMS_FLAT) ? 4 : 3);
-    v6::TraceIO tio{d_rays, d_self_refs, d_hits};
-    return launch_k6(pick_k6<v6::MODE_TRACE>(prims, minb, instrumented), prims, sc, c, jt, nullptr, d_queue, d_counters, sm_count,
-                     stream, false, tune, tio);
+    TraceIO tio{d_rays, d_self_refs, d_hits};
+    if (tune.variant == 6)
+        return launch_k6(pick_k6<v6::MODE_TRACE>(prims, minb, instrumented), prims, sc, c, jt, nullptr, d_queue, d_counters, sm_count,
+                         stream, false, tune, tio);
+    return launch_k5(pick_k5<true>(prims, minb, instrumented), prims, sc, c, jt, nullptr, d_queue, d_counters, sm_count, stream, false,
+                     tune, tio);
 }
 
 }  // namespace rl

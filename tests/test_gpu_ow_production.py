@@ -1,9 +1,11 @@
 """Parity of the PRODUCTION OW loop on the B200 (round-1 verdict, weak 1 / missing 6).
 
-* rl_trace_batch for OW scenes runs through the render kernel itself (k_ow_render6 in trace mode: ready / done rings,
-  big list at ray start, unit directions, the scale-aware t_min, the start-on-surface rule, node steps, leaf rounds), so
-  the hit-id checks below exercise the loop that renders — on the reference's own rays at bounce 0, 1 and 2.
-* every scheduling option of the kernel gives the bit-identical image, and round 1's kernel (v5) the same bits again.
+* rl_trace_batch for OW scenes runs through the render kernel itself (the TRACE instantiation of k_ow_render5: the same
+  work queue, service / refill rounds, big list at ray start, unit directions, the scale-aware t_min, the
+  start-on-surface rule, node steps, leaf rounds), so the hit-id checks below exercise the loop that renders — on the
+  reference's own rays at bounce 0, 1 and 2.
+* every scheduling option of the kernel gives the bit-identical image, and so does the pooled-paths experiment
+  (ow.variant = 6, the shared-memory wavefront that was measured and lost: DESIGN.md §4).
 * rays with exactly zero direction components (ADVICE: inf * 0 in the FMA slab test) hit what the oracle hits.
 * oracle-vs-device images at BASELINE.json's sizes, and a t-test for bias per first-hit material.
 """
@@ -79,6 +81,23 @@ def test_trace_without_self_nodes_equals_self_minus_one(ctx, oracle):
     assert np.array_equal(a["node"], c["node"]) and np.allclose(c["t"][hit] * 4.0, a["t"][hit], rtol=2e-6)
 
 
+def test_trace_is_identical_through_both_kernels(ctx, oracle):
+    """the TRACE instantiations of the production kernel and of the pooled-paths experiment return the same records"""
+    world = scenes.ow_cow_world()
+    desc = ow.lower_world(world)
+    ctx.scene_upload(desc)
+    rays64, sn = oracle.ow_bounce_rays(desc, scenes.ow_cow_params(image_width=120, samples_per_pixel=1).abi(), 1)
+    keep = sn != -2
+    rays, sn = rays64[keep].astype(np.float32), sn[keep]
+    a = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6], rays[:, 6], self_nodes=sn)
+    try:
+        ctx.set_option("ow.variant", 6)
+        b = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6], rays[:, 6], self_nodes=sn)
+    finally:
+        ctx.set_option("ow.variant", 5)
+    assert np.array_equal(a, b) and (a["node"] >= 0).mean() > 0.5
+
+
 def test_axis_aligned_directions(ctx, oracle):
     """Directions with exactly zero components and origins off the axes: 1 / d is clamped to a finite value so that the
     FMA slab test cannot produce inf - inf = NaN and silently miss the whole LBVH (device.cuh safe_rcp)."""
@@ -111,21 +130,21 @@ def test_axis_aligned_directions(ctx, oracle):
 
 OPTION_SETS = [
     {},
-    {"ow.slots": 256},
-    {"ow.slots": 512, "ow.exit_min": 16},
-    {"ow.minb": 3, "ow.exit_min": 4, "ow.svc_lo": 8},
-    {"ow.leaf_min": 4, "ow.svc_lo": 24, "ow.ctas_per_sm": 2},
-    {"ow.variant": 5},
-    {"ow.variant": 5, "ow.svc_min": 8, "ow.leaf_min": 16},
+    {"ow.svc_min": 8, "ow.leaf_min": 16},
+    {"ow.svc_min": 32, "ow.leaf_min": 1, "ow.minb": 3},
+    {"ow.ctas_per_sm": 1},
+    {"ow.variant": 6},
+    {"ow.variant": 6, "ow.slots": 256, "ow.minb": 3, "ow.exit_min": 4, "ow.svc_lo": 8},
+    {"ow.variant": 6, "ow.slots": 512, "ow.exit_min": 16, "ow.leaf_min": 4, "ow.ctas_per_sm": 2},
 ]
-RESET = {"ow.variant": 6, "ow.slots": 0, "ow.minb": 0, "ow.ctas_per_sm": 0, "ow.svc_lo": 0, "ow.exit_min": 0, "ow.leaf_min": 0,
+RESET = {"ow.variant": 5, "ow.slots": 0, "ow.minb": 0, "ow.ctas_per_sm": 0, "ow.svc_lo": 0, "ow.exit_min": 0, "ow.leaf_min": 0,
          "ow.svc_min": 0}
 
 
 @pytest.mark.parametrize("name", ["test_scene", "C4_cover", "C5_cow", "final_scene"])
 def test_every_schedule_and_round1_kernel_give_the_same_bits(ctx, name):
     """The scheduling options move work between warps and rounds; per-path arithmetic and the order samples are folded
-    in are fixed, so the frame is bit-identical — including round 1's per-lane kernel (ow.variant = 5)."""
+    in are fixed, so the frame is bit-identical — including the pooled-paths kernel (ow.variant = 6)."""
     if name == "final_scene":
         world, params = scenes.ow_final_scene(image_width=96, samples_per_pixel=24, max_depth=12)
     else:

@@ -15,7 +15,7 @@ from rendering_learning_b200 import Context, ow, scenes  # noqa: E402
 mode = sys.argv[1] if len(sys.argv) > 1 else "quick"
 ctx = Context(0)
 dev = torch.device("cuda", 0)
-RESET = {"ow.variant": 6, "ow.slots": 0, "ow.minb": 0, "ow.ctas_per_sm": 0, "ow.svc_lo": 0, "ow.exit_min": 0, "ow.leaf_min": 0,
+RESET = {"ow.variant": 5, "ow.slots": 0, "ow.minb": 0, "ow.ctas_per_sm": 0, "ow.svc_lo": 0, "ow.exit_min": 0, "ow.leaf_min": 0,
          "ow.svc_min": 0}
 
 
@@ -51,11 +51,11 @@ def run(name, world, params, grid, reps=3):
     setopts({})
 
 
-v5 = [{"ow.variant": 5}]
+v5 = [{}]
 if mode == "quick":
-    g6 = [{}, {"ow.minb": 3}, {"ow.exit_min": 16}, {"ow.exit_min": 16, "ow.minb": 3}, {"ow.exit_min": 24, "ow.minb": 3}]
-    g5 = [{"ow.variant": 5, "ow.svc_min": a, "ow.leaf_min": b} for a in (16, 20, 24) for b in (6, 8, 12)]
-    g5 += [{"ow.variant": 5, "ow.minb": 3}, {"ow.variant": 5, "ow.minb": 4}]
+    g6 = [{"ow.variant": 6}, {"ow.variant": 6, "ow.exit_min": 16}, {"ow.variant": 6, "ow.exit_min": 24, "ow.minb": 3}]
+    g5 = [{"ow.svc_min": a, "ow.leaf_min": b} for a in (16, 20, 24) for b in (6, 8, 12)]
+    g5 += [{"ow.minb": 3}, {"ow.minb": 4}]
     g6 = g5 + g6
 else:
     g6 = [dict(zip(("ow.minb", "ow.slots", "ow.exit_min", "ow.svc_lo", "ow.leaf_min"), v))
