@@ -62,6 +62,8 @@ enum {
     RL_RTC_GROUP = 8,      /* children[child_begin .. child_end) are node ids                        */
     RL_RTC_BOUNDED = 9,    /* child_begin = child node id                                            */
     RL_RTC_CSG = 10,       /* child_begin = left node id, child_end = right node id, flags = op      */
+    RL_RTC_MESH = 11,      /* WavefrontObj::to_object() of the mesh rl_obj_parse left on the ctx: Bounded<Group<Triangle>>,
+                            * every triangle with `material` (wavefront_obj.rs:164-166 uses Material::default())   */
 
     RL_OW_SPHERE = 32,     /* params: c1[3] c2[3] radius; flags bit0 = moving                        */
     RL_OW_QUAD = 33,       /* params: q[3] u[3] v[3]                                                 */
@@ -70,8 +72,10 @@ enum {
     RL_OW_TRANSLATE = 36,  /* params: offset[3]; child_begin = child node id                          */
     RL_OW_BVH = 37,        /* children[child_begin .. child_end) — Bvh::new(vec)                      */
     RL_OW_LIST = 38,       /* children[child_begin .. child_end) — slice / array of hittables         */
-    RL_OW_CONSTANT_MEDIUM = 39 /* hittable/constant_medium.rs:8-23: params: density; material = the phase
+    RL_OW_CONSTANT_MEDIUM = 39,/* hittable/constant_medium.rs:8-23: params: density; material = the phase
                               * function; child_begin = boundary node id                              */
+    RL_OW_MESH = 40        /* WavefrontObj::to_object(material) of the mesh rl_obj_parse left on the ctx: a Bvh of
+                            * Triangle::from_model(points, texture_coords, normals, material)          */
 };
 
 enum { RL_CSG_UNION = 0, RL_CSG_INTERSECTION = 1, RL_CSG_DIFFERENCE = 2 };
@@ -267,6 +271,31 @@ int rl_scene_info_get(rl_ctx* ctx, rl_scene_info* out);
  * Lets a caller reject a scene the device path cannot lower (RL_E_UNSUPPORTED) before committing to it. */
 int rl_scene_check(const rl_scene_desc* scene, rl_scene_info* out, char* err, int32_t err_cap);
 int rl_lbvh_download(rl_ctx* ctx, rl_lbvh_host* out);
+
+/* ---- OBJ ingest on the device ------------------------------------------------ */
+/* Replaces WavefrontObj::parse (RTC/src/io/wavefront_obj.rs:22-76, OW/src/io/wavefront_obj.rs:32-104) and to_object for
+ * meshes large enough that a sequential host parser is the bottleneck: the OBJ text is copied to the GPU once and parsed
+ * there (lines, records, exact decimal -> f64 conversion, fan triangulation, group replacement order), and a scene node
+ * of kind RL_RTC_MESH / RL_OW_MESH then instances the parsed triangles — transform bake, f32 packing, LBVH input boxes —
+ * on the device as part of rl_scene_upload, so the triangles never visit the host.  `flavor` selects the record set
+ * (OW reads `vt`, RTC ignores it) and the face-index rules of the respective parser.
+ * A ctx holds ONE parsed mesh at a time (a new rl_obj_parse replaces it).  Errors: RL_E_INVALID for a face index that
+ * is out of bounds (the reference panics), RL_E_UNSUPPORTED for a number with more than 19 significant digits or a
+ * decimal exponent beyond +-60 (the only ones the device parser does not convert exactly: it fails rather than round
+ * differently from `str::parse::<f64>`). */
+typedef struct rl_obj_info {
+    int32_t n_vertices, n_normals, n_texcoords; /* `v` / `vn` / `vt` records accepted                 */
+    int32_t n_triangles;                        /* after fan triangulation and group replacement      */
+    int32_t n_groups;                           /* `g` records + the default group                    */
+    int32_t ignored;                            /* WavefrontObj.ignored: lines that yielded nothing   */
+    int32_t kernel_launches;
+    int32_t _pad;
+    double bounds[6];                           /* lo.xyz hi.xyz of the triangles' points (object space) */
+} rl_obj_info;
+int rl_obj_parse(rl_ctx* ctx, const char* text, uint64_t len, int32_t flavor, rl_obj_info* info);
+/* the parsed triangles, for parity checks against the host parser: tri_p [n][3][3], tri_n [n][3][3], tri_uv [n][3][2]
+ * (f64), flags [n] (bit0 = has normals, bit1 = has texture coordinates); any pointer may be NULL */
+int rl_obj_download(rl_ctx* ctx, double* tri_p, double* tri_n, double* tri_uv, uint8_t* flags);
 
 /* ---- ray batches -------------------------------------------------------------------------------- */
 /* RTC: closest hit per `intersect::hit` (RTC/src/scene/intersect.rs:159-168) over `World::intersect`.

@@ -36,6 +36,7 @@ RL_RTC_TRANSFORMED = 7
 RL_RTC_GROUP = 8
 RL_RTC_BOUNDED = 9
 RL_RTC_CSG = 10
+RL_RTC_MESH = 11
 RL_OW_SPHERE = 32
 RL_OW_QUAD = 33
 RL_OW_TRIANGLE = 34
@@ -44,6 +45,7 @@ RL_OW_TRANSLATE = 36
 RL_OW_BVH = 37
 RL_OW_LIST = 38
 RL_OW_CONSTANT_MEDIUM = 39
+RL_OW_MESH = 40
 
 RL_CSG_UNION = 0
 RL_CSG_INTERSECTION = 1
@@ -164,6 +166,12 @@ class rl_job(C.Structure):
                 ("chunk_begin", C.c_int32), ("chunk_end", C.c_int32)]
 
 
+class rl_obj_info(C.Structure):
+    _fields_ = [("n_vertices", C.c_int32), ("n_normals", C.c_int32), ("n_texcoords", C.c_int32), ("n_triangles", C.c_int32),
+                ("n_groups", C.c_int32), ("ignored", C.c_int32), ("kernel_launches", C.c_int32), ("_pad", C.c_int32),
+                ("bounds", C.c_double * 6)]
+
+
 # every symbol include/rl_b200.h declares, with its ctypes signature
 _P = C.c_void_p
 SYMBOLS = {
@@ -181,6 +189,8 @@ SYMBOLS = {
     "rl_scene_info_get": (C.c_int, [_P, C.POINTER(rl_scene_info)]),
     "rl_scene_check": (C.c_int, [C.POINTER(rl_scene_desc), C.POINTER(rl_scene_info), C.c_char_p, C.c_int32]),
     "rl_lbvh_download": (C.c_int, [_P, C.POINTER(rl_lbvh_host)]),
+    "rl_obj_parse": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_int32, C.POINTER(rl_obj_info)]),
+    "rl_obj_download": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint8)]),
     "rl_trace_batch": (C.c_int, [_P, C.POINTER(rl_ray), C.c_uint64, C.POINTER(rl_hit)]),
     "rl_trace_batch_ex": (C.c_int, [_P, C.POINTER(rl_ray), C.POINTER(C.c_int32), C.c_uint64, C.POINTER(rl_hit)]),
     "rl_render_rtc": (C.c_int, [_P, C.POINTER(rl_rtc_camera), C.c_uint32, C.POINTER(C.c_float),

@@ -114,6 +114,25 @@ class Context:
         out["n_prims"], out["n_nodes"] = n, m
         return out
 
+    # ---- OBJ ingest on the device ---------------------------------------------------
+    def obj_parse(self, text, flavor: int) -> A.rl_obj_info:
+        """rl_obj_parse: parse Wavefront OBJ text on the GPU; the triangles stay in HBM and RL_*_MESH nodes instance them"""
+        if isinstance(text, str):
+            text = text.encode()
+        info = A.rl_obj_info()
+        self._check(self.lib.rl_obj_parse(self.h, text, C.c_uint64(len(text)), int(flavor), C.byref(info)))
+        self._scene = None  # a resident scene may reference the previous mesh
+        return info
+
+    def obj_download(self, n_triangles: int) -> dict:
+        p = np.zeros((n_triangles, 3, 3), np.float64)
+        nrm = np.zeros((n_triangles, 3, 3), np.float64)
+        uv = np.zeros((n_triangles, 3, 2), np.float64)
+        fl = np.zeros(n_triangles, np.uint8)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self.lib.rl_obj_download(self.h, dp(p), dp(nrm), dp(uv), fl.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return {"tri_p": p, "tri_n": nrm, "tri_uv": uv, "flags": fl}
+
     # ---- ray batches -------------------------------------------------------------------------
     def trace_batch(self, origins, directions, times=None, self_nodes=None):
         """closest hits of a ray batch; OW rays run through the render kernel's own traversal.  self_nodes (OW): the

@@ -9,6 +9,7 @@
 #include "device.cuh"
 #include "kernels.h"
 #include "lbvh.h"
+#include "obj_ingest.h"
 #include "scene.h"
 
 namespace rl {
@@ -63,6 +64,9 @@ struct rl_ctx {
     int upload_launches = 0;
     // work buffers
     DevBuf counters, queue, jobs, prefix, frame, frame8, partial, rays, hits;
+    ObjMesh mesh;                  // the mesh rl_obj_parse left on this device (RL_RTC_MESH / RL_OW_MESH nodes instance it)
+    rl_obj_info mesh_info{};
+    bool has_mesh = false;
     std::vector<rl_ctx*> group;    // rl_create_multi: [this, peer 1, ...]; empty for a single-GPU ctx
     cudaEvent_t ev_go = nullptr, ev_done = nullptr;  // group renders: leader's "queue is reset", member's "kernel finished"
     OwTuning tune;                 // scheduling parameters of the OW kernel (rl_set_option)
@@ -211,6 +215,7 @@ void rl_destroy(rl_ctx* c) {
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->image_texels) b.release();
     for (DevBuf& b : c->job_tables) b.release();
+    obj_mesh_free(&c->mesh);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_go) cudaEventDestroy(c->ev_go);
@@ -332,7 +337,12 @@ int rl_scene_upload(rl_ctx* c, const rl_scene_desc* scene) {
     c->has_scene = false;
     FlatScene fs;
     std::string err;
-    int rc = flatten_scene(scene, &fs, &err);
+    MeshMeta mm{};
+    if (c->has_mesh) {
+        mm.n_triangles = c->mesh_info.n_triangles;
+        for (int k = 0; k < 6; k++) mm.bounds[k] = c->mesh_info.bounds[k];
+    }
+    int rc = flatten_scene(scene, &fs, &err, c->has_mesh ? &mm : nullptr);
     if (rc != RL_OK) return fail(c, rc, err);
     rc = upload_flat(c, fs, scene->n_nodes);
     // a multi-GPU ctx replicates the scene (and builds the LBVH) on every GPU: <= a few MB, bit-identical builds
@@ -390,6 +400,22 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
     CK(c, upload(c->bvh_ref, fs.bvh_ref, s));
     CK(c, upload(c->bvh_node_id, fs.bvh_node_id, s));
     c->upload_launches = 0;
+    // uses of the device-resident mesh: transform bake, f32 packing and LBVH input boxes of its triangles, on the device
+    for (const FlatScene::MeshUse& u : fs.meshes) {
+        if (!c->has_mesh || u.bvh_first < 0) return fail(c, RL_E_INVALID, "the scene instances a mesh this GPU does not hold");
+        MeshInstance mi{};
+        memcpy(mi.fwd, u.fwd, sizeof(mi.fwd));
+        memcpy(mi.inv, u.inv, sizeof(mi.inv));
+        mi.flavor = fs.flavor;
+        mi.material = u.material;
+        mi.node = u.node;
+        mi.tri_first = u.tri_first;
+        mi.bvh_first = u.bvh_first;
+        mi.xf = u.xf;
+        CK(c, launch_mesh_instance(c->mesh, mi, c->tri_verts.as<TriVerts>(), c->tri_shade.as<TriShade>(), c->bvh_aabb.as<float>(),
+                                   c->bvh_ref.as<int>(), c->bvh_node_id.as<int>(), s));
+        c->upload_launches++;
+    }
     if (n > 0) {
         CK(c, c->bounds.reserve(6 * sizeof(float)));
         CK(c, c->keys.reserve(n * sizeof(uint64_t)));
@@ -476,6 +502,39 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
 
     c->info = scene_info_of(fs);
     c->has_scene = true;
+    return RL_OK;
+}
+
+int rl_obj_parse(rl_ctx* c, const char* text, uint64_t len, int32_t flavor, rl_obj_info* info) {
+    if (!c || (len > 0 && !text)) return RL_E_INVALID;
+    if (flavor != RL_FLAVOR_RTC && flavor != RL_FLAVOR_OW) return fail(c, RL_E_INVALID, "unknown flavor");
+    const size_t members = c->group.empty() ? 1 : c->group.size();
+    for (size_t g = 0; g < members; g++) {  // a multi-GPU ctx parses on every GPU: each one instances its own copy
+        rl_ctx* m = c->group.empty() ? c : c->group[g];
+        CK(c, cudaSetDevice(m->device));
+        obj_mesh_free(&m->mesh);
+        m->has_mesh = false;
+        std::string err;
+        int rc = obj_parse_device(text, len, flavor, m->stream, &m->mesh, &m->mesh_info, &err);
+        if (rc != RL_OK) return fail(c, rc, err);
+        m->has_mesh = true;
+    }
+    CK(c, cudaSetDevice(c->device));
+    if (info) *info = c->mesh_info;
+    return RL_OK;
+}
+
+int rl_obj_download(rl_ctx* c, double* tri_p, double* tri_n, double* tri_uv, uint8_t* flags) {
+    if (!c) return RL_E_INVALID;
+    if (!c->has_mesh) return fail(c, RL_E_INVALID, "no mesh parsed on this ctx");
+    const size_t n = (size_t)c->mesh.n_triangles;
+    if (n == 0) return RL_OK;
+    CK(c, cudaSetDevice(c->device));
+    if (tri_p) CK(c, cudaMemcpyAsync(tri_p, c->mesh.tri_p, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (tri_n) CK(c, cudaMemcpyAsync(tri_n, c->mesh.tri_n, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (tri_uv) CK(c, cudaMemcpyAsync(tri_uv, c->mesh.tri_uv, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (flags) CK(c, cudaMemcpyAsync(flags, c->mesh.tri_flags, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     return RL_OK;
 }
 

@@ -119,10 +119,13 @@ void push_aabb(FlatScene* fs, const double lo[3], const double hi[3], int ref, i
     fs->bvh_node_id.push_back(node);
 }
 
+constexpr int MESH_MARK = 0x7000000;  // leaf-ref index of the placeholder an OW mesh use leaves in the LBVH input
+
 struct Flattener {
     const rl_scene_desc* d;
     FlatScene* fs;
     std::string* err;
+    const MeshMeta* mesh = nullptr;
     int rc = RL_OK;
     int csg_depth = 0;
     // while lowering the boundary of a ConstantMedium, leaves go to medium_refs instead of the LBVH input
@@ -322,6 +325,27 @@ struct Flattener {
                 push_triangle(P, N, nullptr, nd.material, id, (smooth ? 1 : 0) | (xf << 8));
                 return true;
             }
+            case RL_RTC_MESH: {  // io/wavefront_obj.rs:73-76: Bounded<Group<Triangle>> of the ctx's parsed mesh
+                if (csg_depth > 0) return fail(RL_E_UNSUPPORTED, "a device mesh under a Csg is not lowered yet");
+                if (!mesh) return fail(RL_E_INVALID, "RL_RTC_MESH needs a ctx that holds a parsed mesh (rl_obj_parse)");
+                if (!check_material(nd.material)) return false;
+                if (mesh->n_triangles == 0) return true;
+                Aff pat;
+                bool has;
+                if (!pattern_xform(nd.material, inv_total, &pat, &has)) return false;
+                FlatScene::MeshUse* u = mesh_use(fwd_total, inv_total, nd.material, id);
+                if (has) {
+                    Xform x;
+                    store_rows(pat, x.r);
+                    fs->xforms.push_back(x);
+                    u->xf = (int)fs->xforms.size();
+                }
+                u->bvh_first = (int)fs->bvh_ref.size();
+                fs->bvh_aabb.resize(fs->bvh_aabb.size() + 6 * (size_t)mesh->n_triangles, 0.0f);
+                fs->bvh_ref.resize(fs->bvh_ref.size() + (size_t)mesh->n_triangles, 0);
+                fs->bvh_node_id.resize(fs->bvh_node_id.size() + (size_t)mesh->n_triangles, id);
+                return true;
+            }
             case RL_RTC_TRANSFORMED: {
                 const double* q = params(nd, 16);
                 if (!q) return false;
@@ -366,6 +390,31 @@ struct Flattener {
             }
             default:
                 return fail(RL_E_INVALID, "unknown RTC node kind");
+        }
+    }
+
+    // a use of the ctx's device-resident mesh: reserve its triangle slots, remember the transform.  Returns the use.
+    FlatScene::MeshUse* mesh_use(const Aff& fwd, const Aff& inv, int material, int node) {
+        FlatScene::MeshUse u{};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 4; j++) { u.fwd[i][j] = fwd.m[i][j]; u.inv[i][j] = inv.m[i][j]; }
+        u.material = material;
+        u.node = node;
+        u.tri_first = (int)fs->tri_verts.size();
+        u.bvh_first = -1;
+        u.xf = 0;
+        fs->tri_verts.resize(fs->tri_verts.size() + (size_t)mesh->n_triangles, TriVerts{});
+        fs->tri_shade.resize(fs->tri_shade.size() + (size_t)mesh->n_triangles, TriShade{});
+        fs->meshes.push_back(u);
+        return &fs->meshes.back();
+    }
+    // world-space box of the mesh: the 8 transformed corners of its object-space box
+    void mesh_world_box(const Aff& fwd, double lo[3], double hi[3]) const {
+        for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        for (int c = 0; c < 8; c++) {
+            double p[3] = {mesh->bounds[(c & 1) ? 3 : 0], mesh->bounds[(c & 2) ? 4 : 1], mesh->bounds[(c & 4) ? 5 : 2]}, w[3];
+            aff_point(fwd, p, w);
+            for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], w[k]); hi[k] = std::fmax(hi[k], w[k]); }
         }
     }
 
@@ -492,6 +541,19 @@ struct Flattener {
                 push_triangle(P, N, has_uv ? q + 9 : nullptr, nd.material, id, (has_n ? 1 : 0) | (has_uv ? 2 : 0));
                 return true;
             }
+            case RL_OW_MESH: {  // io/wavefront_obj.rs:88-103: Bvh<Triangle<&M>> of the ctx's parsed mesh
+                if (in_boundary) return fail(RL_E_UNSUPPORTED, "a device mesh as the boundary of a ConstantMedium is not lowered yet");
+                if (!mesh) return fail(RL_E_INVALID, "RL_OW_MESH needs a ctx that holds a parsed mesh (rl_obj_parse)");
+                if (!check_material(nd.material)) return false;
+                if (mesh->n_triangles == 0) return fail(RL_E_INVALID, "Cannot make a BVH node without hittables.");
+                mesh_use(fwd, inv, nd.material, id);
+                // ONE placeholder in the LBVH input, with the mesh's world box, so that select_big_prims weighs the walls
+                // around a mesh against the mesh; flatten_scene then swaps it for the mesh's triangle slots
+                double lo[3], hi[3];
+                mesh_world_box(fwd, lo, hi);
+                push_aabb(fs, lo, hi, make_ref(REF_TRI, MESH_MARK + (int)fs->meshes.size() - 1), id);
+                return true;
+            }
             case RL_OW_TRANSFORM: {
                 const double* q = params(nd, 18);
                 if (!q) return false;
@@ -582,19 +644,25 @@ static double box_area(const float* b) {
     double x = (double)b[3] - b[0], y = (double)b[4] - b[1], z = (double)b[5] - b[2];
     return 2.0 * (x * y + y * z + x * z);
 }
-static void select_big_prims(FlatScene* fs) {
+static void select_big_prims(FlatScene* fs, int mesh_triangles) {
     const int n = (int)fs->bvh_ref.size();
     const int room = OW_MAX_BIG - (int)fs->big_refs.size();
-    if (n < 2 * OW_MAX_BIG || room <= 0) return;
+    // a device-resident mesh is ONE placeholder here but stands for all of its triangles
+    const long long n_effective = (long long)n + (long long)fs->meshes.size() * (mesh_triangles > 0 ? mesh_triangles - 1 : 0);
+    if (n_effective < 2 * OW_MAX_BIG || room <= 0) return;
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     auto bigger = [&](int a, int b) {
         double sa = box_area(&fs->bvh_aabb[6 * a]), sb = box_area(&fs->bvh_aabb[6 * b]);
         return sa > sb || (sa == sb && a < b);
     };
-    std::partial_sort(order.begin(), order.begin() + room, order.end(), bigger);
+    auto is_mesh = [&](int i) { return ref_type(fs->bvh_ref[i]) == REF_TRI && ref_index(fs->bvh_ref[i]) >= MESH_MARK; };
+    order.erase(std::remove_if(order.begin(), order.end(), is_mesh), order.end());  // a mesh placeholder is never "big"
+    const int take = std::min(room, (int)order.size());
+    if (take == 0) return;
+    std::partial_sort(order.begin(), order.begin() + take, order.end(), bigger);
     std::vector<char> cand(n, 0);
-    for (int k = 0; k < room; k++) cand[order[k]] = 1;
+    for (int k = 0; k < take; k++) cand[order[k]] = 1;
     float rest[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < n; i++) {
         if (cand[i]) continue;
@@ -606,7 +674,7 @@ static void select_big_prims(FlatScene* fs) {
     const double limit = 0.25 * box_area(rest);
     std::vector<char> big(n, 0);
     bool any = false;
-    for (int k = 0; k < room; k++)
+    for (int k = 0; k < take; k++)
         if (box_area(&fs->bvh_aabb[6 * order[k]]) >= limit) big[order[k]] = 1, any = true;
     if (!any) return;
     std::vector<float> aabb;
@@ -625,7 +693,30 @@ static void select_big_prims(FlatScene* fs) {
     fs->bvh_node_id.swap(node);
 }
 
-int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err) {
+// OW: swap every mesh placeholder of the LBVH input for the mesh's triangle slots (filled on the device)
+static void expand_mesh_placeholders(FlatScene* fs, const MeshMeta* mesh) {
+    if (fs->meshes.empty()) return;
+    std::vector<float> aabb;
+    std::vector<int> ref, node;
+    for (size_t i = 0; i < fs->bvh_ref.size(); i++) {
+        const int r = fs->bvh_ref[i];
+        if (ref_type(r) == REF_TRI && ref_index(r) >= MESH_MARK) continue;
+        aabb.insert(aabb.end(), fs->bvh_aabb.begin() + 6 * i, fs->bvh_aabb.begin() + 6 * i + 6);
+        ref.push_back(r);
+        node.push_back(fs->bvh_node_id[i]);
+    }
+    for (FlatScene::MeshUse& u : fs->meshes) {
+        u.bvh_first = (int)ref.size();
+        aabb.resize(aabb.size() + 6 * (size_t)mesh->n_triangles, 0.0f);
+        ref.resize(ref.size() + (size_t)mesh->n_triangles, 0);
+        node.resize(node.size() + (size_t)mesh->n_triangles, u.node);
+    }
+    fs->bvh_aabb.swap(aabb);
+    fs->bvh_ref.swap(ref);
+    fs->bvh_node_id.swap(node);
+}
+
+int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err, const MeshMeta* mesh) {
     if (!d || d->abi_version != RL_B200_ABI_VERSION) {
         *err = "scene description missing or ABI version mismatch";
         return RL_E_INVALID;
@@ -635,6 +726,7 @@ int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err) {
         return RL_E_INVALID;
     }
     Flattener f{d, out, err};
+    f.mesh = mesh;
     out->flavor = d->flavor;
     out->max_reflection_depth = d->max_reflection_depth;
     for (int k = 0; k < 3; k++) out->void_color[k] = (float)d->void_color[k];
@@ -652,7 +744,8 @@ int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err) {
             return RL_E_INVALID;
         }
         if (!f.ow_node(d->roots[0], aff_identity(), aff_identity(), false, 0)) return f.rc;
-        select_big_prims(out);
+        select_big_prims(out, mesh ? mesh->n_triangles : 0);
+        expand_mesh_placeholders(out, mesh);
     }
     return RL_OK;
 }

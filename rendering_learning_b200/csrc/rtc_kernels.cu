@@ -330,7 +330,8 @@ struct RtcTracer {
                 float t, b1, b2;
                 if (tri_hit(pre, f3(p0), f3(p1), f3(p2), &t, &b1, &b2)) {
                     int node = __float_as_int(p1.w);
-                    if (t >= 0.0f && (t < hp->t || (t == hp->t && node >= hp->node))) {
+                    // ties: later leaf wins; the triangles of one device-ingested mesh share a node, their order is ti
+                    if (t >= 0.0f && (t < hp->t || (t == hp->t && (node > hp->node || (node == hp->node && (hp->prim >= 0 || ti >= ~hp->prim)))))) {
                         hp->t = t;
                         hp->prim = ~ti;
                         hp->node = node;

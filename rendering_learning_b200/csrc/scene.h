@@ -168,9 +168,22 @@ struct FlatScene {
     int has_transparency = 0;
     int max_reflection_depth = 5;
     float void_color[3] = {0, 0, 0};
+    // uses of the ctx's device-resident mesh (RL_RTC_MESH / RL_OW_MESH): the flattener only RESERVES their triangle slots
+    // (zero-filled here) and records the composed transform; obj_ingest.cu's k_mesh_instance fills them on the device
+    struct MeshUse {
+        double fwd[3][4], inv[3][4];
+        int material, node, tri_first, bvh_first, xf;
+    };
+    std::vector<MeshUse> meshes;
 };
 
-// returns RL_OK or an RL_E_* code and fills `err`
-int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err);
+// what the flattener may know about the ctx's parsed mesh: its size and object-space extent, never its triangles
+struct MeshMeta {
+    int n_triangles;
+    double bounds[6];
+};
+
+// returns RL_OK or an RL_E_* code and fills `err`; `mesh` = the ctx's parsed mesh (nullptr: RL_*_MESH nodes are an error)
+int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err, const MeshMeta* mesh = nullptr);
 
 }  // namespace rl

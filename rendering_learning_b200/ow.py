@@ -451,6 +451,23 @@ class Bvh(Hittable):
         return me
 
 
+class DeviceMesh(Hittable):
+    """`WavefrontObj::parse(reader).to_object(material)` (io/wavefront_obj.rs:32-104) with the OBJ text parsed ON THE GPU
+    (Context.obj_parse): the scene node only names the mesh the ctx holds, its triangles never visit the host."""
+
+    def __init__(self, info, material: Material):
+        self.info, self.material = info, material
+
+    @classmethod
+    def parse(cls, text, material: Material, ctx=None) -> "DeviceMesh":
+        from .context import default_context
+        ctx = ctx or default_context()
+        return cls(ctx.obj_parse(text, A.RL_FLAVOR_OW), material)
+
+    def _lower(self, sd):
+        return sd.add_node(A.RL_OW_MESH, material=self.material._lower(sd))
+
+
 class HittableList(Hittable):
     """A slice / array of hittables (`impl Hittable for [H]`, hittable/mod.rs:86-111)."""
 

@@ -419,6 +419,25 @@ class Bounded(Object):
         return me
 
 
+class DeviceMesh(Object):
+    """`WavefrontObj::parse(reader).to_object()` (io/wavefront_obj.rs:22-76) with the OBJ text parsed ON THE GPU
+    (Context.obj_parse): a Bounded<Group<Triangle>> whose triangles never visit the host.  Every triangle
+    gets Material::default() (wavefront_obj.rs:164-166) unless another material is given."""
+
+    def __init__(self, info, material=None):
+        self.info = info
+        self.material = material if material is not None else Material()
+
+    @classmethod
+    def parse(cls, text, ctx=None, material=None) -> "DeviceMesh":
+        from .context import default_context
+        ctx = ctx or default_context()
+        return cls(ctx.obj_parse(text, A.RL_FLAVOR_RTC), material)
+
+    def _lower(self, sd):
+        return sd.add_node(A.RL_RTC_MESH, material=self.material._lower(sd))
+
+
 class CsgOperation:
     Union = A.RL_CSG_UNION
     Intersection = A.RL_CSG_INTERSECTION

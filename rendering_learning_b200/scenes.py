@@ -430,19 +430,22 @@ def ow_spot_texture() -> np.ndarray:
     return ow.srgb.srgb_to_linear(f).astype(np.float32)
 
 
-def ow_cow_world():
-    """OW/examples/cow.rs:17-117 — Cornell box + textured spot (BASELINE config C5)."""
+def ow_cow_world(cow=None):
+    """OW/examples/cow.rs:17-117 — Cornell box + textured spot (BASELINE config C5).  `cow`: the mesh object (e.g. an
+    ow.DeviceMesh parsed on the GPU) instead of the host-parsed fixture."""
     from . import ow
-    m = load_mesh("spot")
-    cow_surface = ow.Lambertian(ow.Image(ow_spot_texture()))
-    tris = []
-    P, UV, N = m["tri_p"], m["tri_uv"], m["tri_n"]
-    for i in range(P.shape[0]):
-        pts = [tuple(P[i, k]) for k in range(3)]
-        uv = [tuple(UV[i, k]) for k in range(3)] if m["has_uv"][i] else None
-        ns = [tuple(N[i, k]) for k in range(3)] if m["has_n"][i] else None
-        tris.append(ow.Triangle.from_model(pts, uv, ns, cow_surface))
-    cow = ow.Bvh.new(tris).scale(200.0).rotate_y(45.0).translate(ow.Vec3(240.0, 165.0, 240.0))
+    if cow is None:
+        m = load_mesh("spot")
+        cow_surface = ow.Lambertian(ow.Image(ow_spot_texture()))
+        tris = []
+        P, UV, N = m["tri_p"], m["tri_uv"], m["tri_n"]
+        for i in range(P.shape[0]):
+            pts = [tuple(P[i, k]) for k in range(3)]
+            uv = [tuple(UV[i, k]) for k in range(3)] if m["has_uv"][i] else None
+            ns = [tuple(N[i, k]) for k in range(3)] if m["has_n"][i] else None
+            tris.append(ow.Triangle.from_model(pts, uv, ns, cow_surface))
+        cow = ow.Bvh.new(tris)
+    cow = cow.scale(200.0).rotate_y(45.0).translate(ow.Vec3(240.0, 165.0, 240.0))
     red = ow.Lambertian(ow.SolidColor(ow.Color(0.65, 0.05, 0.05)))
     white = ow.Lambertian(ow.SolidColor(ow.Color(0.73, 0.73, 0.73)))
     green = ow.Lambertian(ow.SolidColor(ow.Color(0.12, 0.45, 0.15)))

@@ -29,6 +29,7 @@ pub const RL_RTC_TRANSFORMED: i32 = 7;
 pub const RL_RTC_GROUP: i32 = 8;
 pub const RL_RTC_BOUNDED: i32 = 9;
 pub const RL_RTC_CSG: i32 = 10;
+pub const RL_RTC_MESH: i32 = 11;
 pub const RL_OW_SPHERE: i32 = 32;
 pub const RL_OW_QUAD: i32 = 33;
 pub const RL_OW_TRIANGLE: i32 = 34;
@@ -37,6 +38,7 @@ pub const RL_OW_TRANSLATE: i32 = 36;
 pub const RL_OW_BVH: i32 = 37;
 pub const RL_OW_LIST: i32 = 38;
 pub const RL_OW_CONSTANT_MEDIUM: i32 = 39;
+pub const RL_OW_MESH: i32 = 40;
 
 pub const RL_CSG_UNION: i32 = 0;
 pub const RL_CSG_INTERSECTION: i32 = 1;
@@ -251,6 +253,20 @@ pub struct rl_job {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct rl_obj_info {
+    pub n_vertices: i32,
+    pub n_normals: i32,
+    pub n_texcoords: i32,
+    pub n_triangles: i32,
+    pub n_groups: i32,
+    pub ignored: i32,
+    pub kernel_launches: i32,
+    pub _pad: i32,
+    pub bounds: [f64; 6],
+}
+
+#[repr(C)]
 pub struct rl_ctx {
     _opaque: [u8; 0],
 }
@@ -271,6 +287,9 @@ extern "C" {
     pub fn rl_scene_info_get(ctx: *mut rl_ctx, out: *mut rl_scene_info) -> c_int;
     pub fn rl_scene_check(scene: *const rl_scene_desc, out: *mut rl_scene_info, err: *mut c_char, err_cap: i32) -> c_int;
     pub fn rl_lbvh_download(ctx: *mut rl_ctx, out: *mut rl_lbvh_host) -> c_int;
+
+    pub fn rl_obj_parse(ctx: *mut rl_ctx, text: *const c_char, len: u64, flavor: i32, info: *mut rl_obj_info) -> c_int;
+    pub fn rl_obj_download(ctx: *mut rl_ctx, tri_p: *mut f64, tri_n: *mut f64, tri_uv: *mut f64, flags: *mut u8) -> c_int;
 
     pub fn rl_trace_batch(ctx: *mut rl_ctx, rays: *const rl_ray, n: u64, out: *mut rl_hit) -> c_int;
     pub fn rl_trace_batch_ex(ctx: *mut rl_ctx, rays: *const rl_ray, self_nodes: *const i32, n: u64, out: *mut rl_hit) -> c_int;

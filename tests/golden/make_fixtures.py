@@ -64,6 +64,15 @@ def main():
     np.savez_compressed(os.path.join(ASSETS, "spot.npz"), tri_p=P, tri_uv=UV, tri_n=N, has_uv=HUV, has_n=HN)
     print("spot", P.shape, int(HUV.sum()), "with uv", int(HN.sum()), "with normals")
 
+    # the OBJ TEXT itself (input data named by BASELINE.json's north_star), gzip-compressed: what the device-side OBJ
+    # ingest parses on the GPU box, where /root/reference does not exist
+    import gzip
+    for name in ("teapot-low.obj", "spot_triangulated.obj"):
+        raw = open(os.path.join(REF, "objs", name), "rb").read()
+        with gzip.GzipFile(os.path.join(GOLD, name + ".gz"), "wb", mtime=0) as f:
+            f.write(raw)
+        print(name, len(raw), "bytes")
+
     from PIL import Image
     im = np.array(Image.open(os.path.join(REF, "objs/spot_texture.png")).convert("RGB"), np.uint8)
     np.savez_compressed(os.path.join(ASSETS, "spot_texture.npz"), rgb8=im)

@@ -168,3 +168,14 @@ def test_random_rtc_trees_lower_every_leaf_once(data):
     objs = [_rtc_tree(data.draw, 0, counter, False) for _ in range(data.draw(st.integers(1, 3)))]
     info = rtc.World(objects=objs, lights=[rtc.PointLight((0, 5, -5), (1, 1, 1))]).lower().check()
     assert (info.n_prims, info.n_bvh_prims) == (counter[0], counter[1])
+
+
+def test_device_mesh_nodes_need_a_ctx_that_holds_a_mesh():
+    """RL_RTC_MESH / RL_OW_MESH name the mesh rl_obj_parse left on a ctx; the host-only check has none"""
+    from rendering_learning_b200 import RlError, ow, rtc
+    sd = ow.lower_world([ow.DeviceMesh(None, ow.Lambertian(ow.SolidColor((0.5, 0.5, 0.5))))])
+    with pytest.raises(RlError, match="parsed mesh"):
+        sd.check()
+    w = rtc.World(objects=[rtc.DeviceMesh(None)], lights=[])
+    with pytest.raises(RlError, match="parsed mesh"):
+        w.lower().check()
