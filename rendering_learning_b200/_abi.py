@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librl_b200.so")
+# RL_B200_DEBUG=1 loads the bounds-asserting build (librl_b200_debug.so, `__graft_entry__.build(debug=True)`): the same
+# CUDA code with every index checked against the scene's counts — still the device path, never a CPU one
+LIB_PATH = os.path.join(HERE, "librl_b200_debug.so" if os.environ.get("RL_B200_DEBUG") == "1" else "librl_b200.so")
 
 RL_B200_ABI_VERSION = 3
 RL_QUEUE_SLOTS = 2

@@ -55,6 +55,31 @@ __device__ __forceinline__ float3 xf_normal(const float4 r[3], float3 n) {
               fmaf(r[0].z, n.x, fmaf(r[1].z, n.y, r[2].z * n.z)));
 }
 
+// ---- bounds-asserting debug build (-DRL_DEBUG: librl_b200_debug.so, tools/sanitize_small.py) -------------------------------
+// compute-sanitizer is closed on this pool, so the debug library checks every index the kernels form against the scene's
+// own counts; a failed check bumps the overflow counter (the render then fails with RL_E_OVERFLOW) instead of reading or
+// writing out of bounds.  In the release build RL_CHECK compiles to nothing.
+#ifdef RL_DEBUG
+#define RL_CHECK(cond, lc)        \
+    do {                          \
+        if (!(cond)) (lc).overflow += 1u << 20; \
+    } while (0)
+#define RL_CHECK_OR(cond, lc, stmt) \
+    do {                            \
+        if (!(cond)) {              \
+            (lc).overflow += 1u << 20; \
+            stmt;                   \
+        }                           \
+    } while (0)
+#else
+#define RL_CHECK(cond, lc) \
+    do {                   \
+    } while (0)
+#define RL_CHECK_OR(cond, lc, stmt) \
+    do {                            \
+    } while (0)
+#endif
+
 // ---- counters (instrumented builds only) ----------------------------------------------------------------
 struct Counters {
     unsigned long long rays, node_visits, prim_tests, tri_tests, shades, overflow;
@@ -167,6 +192,7 @@ __device__ __forceinline__ void bvh_traverse(const BvhNode* __restrict__ nodes, 
     int sp = 0;
     int node = 0;
     while (true) {
+        RL_CHECK_OR(node >= 0 && node < (n_bvh_prims > 1 ? n_bvh_prims - 1 : 1), lc, return);
         const float4* np = reinterpret_cast<const float4*>(nodes + node);
         float4 a = np[0], b = np[1], c = np[2];
         int4 d = *reinterpret_cast<const int4*>(np + 3);
@@ -319,7 +345,8 @@ __device__ __forceinline__ float2 ffma2(float2 a, float s, float t) { return ffm
 template <bool COUNT, int THREADS>
 __device__ __forceinline__ void bvh2_step(const BvhNode* __restrict__ nodes, int& node, TravStack& st, StackSpill& spill,
                                           const float3 inv_d, const float3 oi, const float tmin, const float tmax,
-                                          LocalCount<COUNT>& lc) {
+                                          LocalCount<COUNT>& lc, const int n_nodes = 0x7fffffff) {
+    RL_CHECK_OR(node >= 0 && node < n_nodes, lc, { node = TRAV_END; return; });
     const float4* np = reinterpret_cast<const float4*>(nodes + node);
     const float4 a = np[0], b = np[1], c = np[2];
     const int2 d = *reinterpret_cast<const int2*>(np + 3);

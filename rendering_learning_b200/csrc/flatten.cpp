@@ -290,7 +290,6 @@ struct Flattener {
                 return true;
             }
             case RL_RTC_TRIANGLE: {
-                if (csg_depth > 0) return fail(RL_E_UNSUPPORTED, "triangles under a Csg are not lowered yet");
                 if (!check_material(nd.material)) return false;
                 const double* q = params(nd, 18);
                 if (!q) return false;
@@ -321,6 +320,25 @@ struct Flattener {
                     store_rows(pat, x.r);
                     fs->xforms.push_back(x);
                     xf = (int)fs->xforms.size();  // index + 1
+                }
+                if (csg_depth > 0) {
+                    // a leaf of a Csg (csg.rs:31-35 takes any Object): an analytic primitive inside the Csg's contiguous leaf
+                    // range — world-space vertices, normals, world -> pattern space (rtc_kernels.cu tri_prim_roots)
+                    if (has) fs->xforms.pop_back();
+                    RtcPrim p{};
+                    for (int k = 0; k < 3; k++) {
+                        p.inv[k] = make_float4((float)P[k][0], (float)P[k][1], (float)P[k][2], 0.0f);
+                        p.fwd[k] = make_float4((float)N[k][0], (float)N[k][1], (float)N[k][2], 0.0f);
+                    }
+                    store_rows(has ? pat : aff_identity(), p.pat);
+                    p.ymin = -INFINITY;
+                    p.ymax = INFINITY;
+                    p.kind = PK_TRIANGLE;
+                    p.flags = smooth ? 1 : 0;
+                    p.material = nd.material;
+                    p.node = id;
+                    fs->prims.push_back(p);
+                    return true;
                 }
                 push_triangle(P, N, nullptr, nd.material, id, (smooth ? 1 : 0) | (xf << 8));
                 return true;
@@ -732,9 +750,9 @@ int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err, cons
     for (int k = 0; k < 3; k++) out->void_color[k] = (float)d->void_color[k];
     if (!f.lower_tables()) return f.rc;
     if (d->flavor == RL_FLAVOR_RTC) {
-        if (d->max_reflection_depth < 0 || d->max_reflection_depth > 16) {
-            *err = "max_reflection_depth must be in [0, 16] on the device path";
-            return RL_E_UNSUPPORTED;
+        if (d->max_reflection_depth < 0) {  // World.max_reflection_depth is a usize (world.rs:29): any non-negative value
+            *err = "max_reflection_depth must be >= 0";
+            return RL_E_INVALID;
         }
         for (int k = 0; k < d->n_roots; k++)
             if (!f.rtc_node(d->roots[k], aff_identity(), aff_identity(), 0)) return f.rc;

@@ -147,6 +147,8 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
                                              int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc, unsigned ray_rnd = 0u) {
     const float3 o = pre.o, d = pre.d;
     int type = ref_type(ref), idx = ref_index(ref);
+    RL_CHECK_OR(ref >= 0 && idx < (type == REF_SPHERE ? sc.n_spheres : type == REF_TRI ? sc.n_tris : type == REF_QUAD ? sc.n_quads : sc.n_media),
+                lc, return);
     if ((PRIMS & PRIMS_MEDIA) && type == REF_MEDIUM) {
         ow_medium_test<COUNT, PRIMS>(sc, ref, pre, a_dd, time, tmin, ray_rnd, h, lc);
         return;
@@ -378,6 +380,7 @@ __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, P
     }
     bool front = in_medium || dot(p.d, outward) <= 0.0f;  // hittable/mod.rs:32-38 (a medium hit is Face::Front)
     normal = front ? outward : -outward;
+    RL_CHECK_OR(mat_id >= 0 && mat_id < sc.n_materials, lc, return false);
     const DevMaterial m = sc.materials[mat_id];
     int kind = __float_as_int(m.b.w);
     int tex = __float_as_int(m.color.w);
@@ -578,6 +581,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             // ONE 16-byte store per finished item (over NVLink when the buffer is rank 0's: three 4-byte stores per
             // item were 134 M small remote writes per 8-GPU cover-scene step)
             size_t idx = ((size_t)sm_chunk[tid] * cam.height + sm_y[tid]) * cam.width + sm_x[tid];
+            RL_CHECK(sm_chunk[tid] >= 0 && sm_chunk[tid] < cam.n_chunks && sm_x[tid] < cam.width && sm_y[tid] < cam.height, lc);
             reinterpret_cast<float4*>(partial)[idx] = make_float4(sm_acc[0][tid], sm_acc[1][tid], sm_acc[2][tid], 0.0f);
             has_item = false;
             retired++;
@@ -722,7 +726,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 // 4 -> 12.63 / 65.4: two halve the ballots while a lane that parks after the first step idles one step only)
 #pragma unroll
                 for (int k = 0; k < (OPT < 1 ? 1 : OPT); k++) {
-                    if (node >= 0) bvh2_step<COUNT, 256>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc);
+                    if (node >= 0) bvh2_step<COUNT, 256>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc, sc.n_bvh_nodes);
                 }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);
@@ -1176,7 +1180,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
             do {
 #pragma unroll
                 for (int k = 0; k < 2; k++) {  // two steps per ballot (measured in round 1: 1 / 2 / 3 / 4 -> 12.44 / 12.11 / 12.39 / 12.63 ms)
-                    if (node >= 0) bvh2_step<COUNT, THREADS>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc);
+                    if (node >= 0) bvh2_step<COUNT, THREADS>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc, sc.n_bvh_nodes);
                 }
                 n_in = __popc(__ballot_sync(FULL, node >= 0));
             } while (n_in > keep && n_in > 0);

@@ -22,7 +22,11 @@ namespace {
 
 constexpr float RTC_EPS = 1e-8f;       // plane / cylinder / cone epsilons of the reference
 constexpr float RTC_BIAS = 1e-5f;      // POINT_OFFSET_BIAS (intersect.rs:8)
-constexpr int RTC_STACK = 18;          // max_reflection_depth <= 16
+// Pending (ray, weight, depth) entries of the unrolled recursion.  An entry is popped before its children are pushed, so the
+// stack only grows where a hit pushes BOTH a reflected and a refracted ray: a mirror-only chain of any depth needs one
+// entry.  66 entries = 64 such levels pending at once (a tree the reference itself could not finish); beyond that the
+// render reports RL_E_OVERFLOW instead of a wrong image.  max_reflection_depth itself is unbounded, as in world.rs:29.
+constexpr int RTC_STACK = 66;
 
 struct RtcCam {
     int hsize, vsize;
@@ -140,6 +144,19 @@ __device__ __forceinline__ int prim_roots(const RtcPrim& p, float3 o, float3 d, 
     return n;
 }
 
+// A triangle that is a leaf of a Csg (csg.rs:31-35 is generic over any Object) travels as an analytic primitive: its
+// world-space vertices in inv[0..2], its normals in fwd[0..2] (flat: fwd[0] = the face normal), world -> pattern space in
+// pat, flags bit0 = smooth.  Same watertight test as the LBVH triangles; one root, of either sign (triangle.rs:63-101).
+__device__ __forceinline__ int tri_prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], float* b1, float* b2) {
+    RayPre pre = make_pre(o, d);
+    float t, u, v;
+    if (!tri_hit(pre, f3(p.inv[0]), f3(p.inv[1]), f3(p.inv[2]), &t, &u, &v)) return 0;
+    ts[0] = t;
+    *b1 = u;
+    *b2 = v;
+    return 1;
+}
+
 // local normal (PhysicalObject::normal_at) and the local hit point snapped back onto the surface, so the
 // world-space point carries ~1 ulp of error instead of the error of t (keeps the 1e-5 bias meaningful)
 __device__ __forceinline__ float3 prim_normal(const RtcPrim& p, float3& q, int tag) {
@@ -250,17 +267,26 @@ struct RtcTracer {
                 i++;
                 continue;
             }
+            RL_CHECK_OR(p.csg_first >= 0 && p.csg_first + p.csg_count <= sc.n_csg, lc, return);
             const int4 top = sc.csg[p.csg_first + p.csg_count - 1];
+            RL_CHECK_OR(top.y >= 0 && top.w <= sc.n_prims && top.y <= top.w, lc, return);
             float ct[CSG_CAP];
             int ci[CSG_CAP];  // prim << 8 | tag
             int cn = 0;
             for (int j = top.y; j < top.w; j++) {
                 const RtcPrim& q = sc.prims[j];
-                float3 lo = xf_point(q.inv, o), ld = xf_vec(q.inv, d);
                 float ts[4];
-                unsigned tags;
-                int n = prim_roots(q, lo, ld, ts, &tags);
-                if (COUNT) lc.prims++;
+                unsigned tags = 0u;
+                int n;
+                if (q.kind == PK_TRIANGLE) {
+                    float b1, b2;
+                    n = tri_prim_roots(q, o, d, ts, &b1, &b2);
+                    if (COUNT) lc.tris++;
+                } else {
+                    float3 lo = xf_point(q.inv, o), ld = xf_vec(q.inv, d);
+                    n = prim_roots(q, lo, ld, ts, &tags);
+                    if (COUNT) lc.prims++;
+                }
                 for (int k = 0; k < n; k++) {
                     if (cn >= CSG_CAP) { lc.overflow++; break; }
                     // stable insertion by t
@@ -325,6 +351,7 @@ struct RtcTracer {
             RtcHit* hp = &h;
             bvh_traverse<COUNT>(sc.nodes, sc.n_bvh_prims, pre, 0.0f, h.t, lc, [&](int ref, float tmax) -> float {
                 int ti = ref_index(ref);
+                RL_CHECK_OR(ref_type(ref) == REF_TRI && ti < sc.n_tris, lcr, return tmax);
                 float4 p0 = tv[ti].p0, p1 = tv[ti].p1, p2 = tv[ti].p2;
                 if (COUNT) lcr.tris++;
                 float t, b1, b2;
@@ -569,7 +596,16 @@ struct RtcTracer {
             // ---- prepare_computations (intersect.rs:47-70) ----
             float3 point, normal, pat_p;
             int mat_id;
-            if (h.prim >= 0) {
+            if (CSG && h.prim >= 0 && sc.prims[h.prim].kind == PK_TRIANGLE) {
+                const RtcPrim& p = sc.prims[h.prim];
+                float ts[4], b1 = 0.0f, b2 = 0.0f;
+                tri_prim_roots(p, o, d, ts, &b1, &b2);  // the barycentrics of the hit (the crossing list keeps t only)
+                const float b0 = 1.0f - b1 - b2;
+                point = f3(p.inv[0]) * b0 + f3(p.inv[1]) * b1 + f3(p.inv[2]) * b2;
+                normal = (p.flags & 1) ? normalize_precise(f3(p.fwd[1]) * b1 + f3(p.fwd[2]) * b2 + f3(p.fwd[0]) * b0) : f3(p.fwd[0]);
+                mat_id = p.material;
+                pat_p = xf_point(p.pat, point);
+            } else if (h.prim >= 0) {
                 const RtcPrim& p = sc.prims[h.prim];
                 float3 lo = xf_point(p.inv, o), ld = xf_vec(p.inv, d);
                 float3 q = fma3(ld, h.t, lo);
@@ -596,8 +632,10 @@ struct RtcTracer {
                 int xf = flags >> 8;
                 pat_p = xf > 0 ? xf_point(sc.xforms[xf - 1].r, point) : point;
             }
+            RL_CHECK_OR(mat_id >= 0 && mat_id < sc.n_materials, lc, continue);
             const DevMaterial m = sc.materials[mat_id];
             int tex = __float_as_int(m.color.w);
+            RL_CHECK_OR(tex < sc.n_textures, lc, continue);
             float3 obj_color = tex >= 0 ? pattern_at(sc.textures[tex], pat_p) : f3(m.color);
             float3 eyev = normalize_precise(-d);
             if (dot(normal, eyev) < 0.0f) normal = -normal;

@@ -167,15 +167,80 @@ def test_void_cases(ctx, oracle):
 def test_error_behaviour(ctx):
     with pytest.raises(ValueError, match="not invertible"):
         rtc.Transformed.new(rtc.Sphere(), T.scaling(0, 1, 1))
-    with pytest.raises(RlError) as e:  # a mesh under a Csg is the one RTC construct not lowered
-        tri = rtc.Triangle.flat([(0, 0, 0), (1, 0, 0), (0, 1, 0)])
-        w = rtc.World(objects=[rtc.Csg(rtc.Sphere(), tri, rtc.CsgOperation.Union)], lights=[rtc.PointLight((0, 5, -5), (1, 1, 1))])
-        rtc.Scene(scenes.rtc_mirror_scene(8, 8).camera, w).render(ctx=ctx)
-    assert e.value.code == A.RL_E_UNSUPPORTED
     w = scenes.rtc_mirror_world()
-    w.max_reflection_depth = 99
+    w.max_reflection_depth = -1
     with pytest.raises(RlError):
         rtc.Scene(scenes.rtc_mirror_scene(8, 8).camera, w).render(ctx=ctx)
+
+
+def test_max_reflection_depth_is_unbounded(ctx, oracle):
+    """World.max_reflection_depth is a usize (world.rs:26-31).  The unrolled stack only grows where a hit spawns BOTH a
+    reflected and a refracted ray, so a hall of mirrors at depth 99 (round 1 refused > 16) needs one entry and matches
+    the oracle.  (Mirrors only: with reflective AND transparent surfaces the reference's own recursion is 2^depth.)"""
+    mat = lambda c, **k: rtc.Material(surface=c, **k)
+    mirror = dict(reflectivity=0.9, diffuse=0.1, ambient=0.05, specular=0.0)
+    objects = [rtc.Transformed.new(rtc.Plane(mat((0.9, 0.9, 1.0), **mirror)), T.sequence([T.rotation_x(math.pi / 2), T.translation(0, 0, 4)])),
+               rtc.Transformed.new(rtc.Plane(mat((1.0, 0.9, 0.9), **mirror)), T.sequence([T.rotation_x(math.pi / 2), T.translation(0, 0, -6)])),
+               rtc.Plane(mat(rtc.Checker3d(a=(0.8, 0.8, 0.8), b=(0.2, 0.2, 0.2), transform=T.translation(0.0, -0.01, 0.0)))),
+               rtc.Transformed.new(rtc.Sphere(mat((0.9, 0.2, 0.2))), T.translation(0.6, 1.0, 0.0))]
+    cam = rtc.Camera.new(120, 80, 1.0, T.view_transform((-0.5, 1.2, -5.0), (0.3, 1.0, 0.0), (0, 1, 0)))
+    imgs = {}
+    for depth in (5, 99):
+        w = rtc.World(objects=objects, lights=[rtc.PointLight((-2, 6, -3), (1, 1, 1))], max_reflection_depth=depth)
+        frac, img, ref = image_parity(ctx, oracle, rtc.Scene(cam, w))
+        assert frac <= 5e-3, (depth, frac)  # long reflection chains amplify the f32 / f64 difference at a few floor pixels
+        imgs[depth] = img
+    assert np.abs(imgs[99] - imgs[5]).max() > 1e-4  # the bounces beyond the fifth are really traced
+
+
+def csg_mesh_scene(w=300, h=200):
+    """Csg<T> is generic over any Object (csg.rs:31-35): triangles as Csg leaves — a tetrahedron (flat) carved out of a cube,
+    a smooth-shaded fan intersected with a sphere, and the teapot (Bounded<Group<Triangle>>) cut by a slab"""
+    mat = lambda c, **k: rtc.Material(surface=c, **k)
+    P = [(0.0, 1.2, 0.0), (-1.1, -0.6, -1.1), (1.1, -0.6, -1.1), (0.0, -0.6, 1.2)]
+    tetra = rtc.Group.new([rtc.Triangle.flat([P[a], P[b], P[c]], mat((0.9, 0.3, 0.2))) for a, b, c in
+                           ((0, 1, 2), (0, 2, 3), (0, 3, 1), (1, 3, 2))])
+    carved = rtc.Csg(rtc.Cube(mat((0.3, 0.6, 0.9))), rtc.Transformed.new(tetra, T.scaling(1.2, 1.2, 1.2)), rtc.CsgOperation.Difference)
+    top, ring = (0.0, 1.5, 0.0), [(math.cos(a) * 1.2, 0.0, math.sin(a) * 1.2) for a in np.linspace(0, 2 * math.pi, 7)[:-1]]
+    nrm = lambda p: tuple(np.array(p) / np.linalg.norm(p))
+    fan = [rtc.Triangle.smooth([(top, (0.0, 1.0, 0.0)), (ring[(k + 1) % 6], nrm(ring[(k + 1) % 6])), (ring[k], nrm(ring[k]))],
+                               mat(rtc.Stripe(a=(0.9, 0.9, 0.2), b=(0.2, 0.5, 0.2), transform=T.scaling(0.25, 0.25, 0.25))))
+           for k in range(6)]
+    base = rtc.Triangle.flat([ring[0], ring[2], ring[4]], mat((0.5, 0.5, 0.5)))
+    cone_mesh = rtc.Group.new(fan + [base])
+    capped = rtc.Csg(rtc.Transformed.new(rtc.Sphere(mat((0.7, 0.2, 0.7), reflectivity=0.3)), T.translation(0.0, 0.4, 0.0)),
+                     cone_mesh, rtc.CsgOperation.Intersection)
+    teapot_cut = rtc.Csg(rtc.Transformed.new(scenes.rtc_teapot_object(), T.sequence([T.rotation_x(-math.pi / 2), T.scaling(0.12, 0.12, 0.12)])),
+                         rtc.Transformed.new(rtc.Cube(mat((0.9, 0.9, 0.9))), T.sequence([T.scaling(3, 0.5, 3), T.translation(0, 1.75, 0)])),
+                         rtc.CsgOperation.Difference)
+    world = rtc.World(
+        objects=[rtc.Plane(mat((0.8, 0.8, 0.75), specular=0.1)),
+                 rtc.Transformed.new(carved, T.sequence([T.rotation_y(0.6), T.translation(-3.0, 1.0, 0.5)])),
+                 rtc.Transformed.new(capped, T.sequence([T.rotation_y(-0.4), T.translation(0.2, 0.6, -1.0)])),
+                 rtc.Transformed.new(teapot_cut, T.sequence([T.rotation_y(0.5), T.translation(3.0, 0.0, 1.0)]))],
+        lights=[rtc.PointLight((-6, 8, -6), (0.7, 0.7, 0.7)), rtc.PointLight((5, 7, -5), (0.3, 0.3, 0.3))],
+        max_reflection_depth=3)
+    cam = rtc.Camera.new(w, h, 1.0, T.view_transform((0.5, 3.5, -8.0), (0, 0.8, 0), (0, 1, 0)))
+    return rtc.Scene(camera=cam, world=world)
+
+
+def test_triangles_under_csg(ctx, oracle):
+    """round 1 refused triangles below a Csg (RL_E_UNSUPPORTED); they are Csg leaves like any other shape now.  The device
+    intersects them watertight where the reference uses Moller-Trumbore: mismatches can only sit on triangle edges."""
+    sc = csg_mesh_scene()
+    desc = sc.world.lower()
+    ctx.scene_upload(desc)
+    cam = sc.camera.abi()
+    img, st = ctx.render_rtc(cam, 1)
+    assert st.overflow == 0
+    ref = oracle.rtc_render(desc, cam, 1)
+    bad = (np.abs(u8(img.astype(np.float64)) - u8(ref)) > 1).any(axis=2)
+    assert bad.mean() <= 2e-3, bad.mean()
+    mism, rel, node = trace_parity(ctx, oracle, desc, oracle.rtc_camera_rays(cam, 1))
+    assert mism.mean() <= 2e-4, mism.sum()
+    assert np.quantile(rel, 0.9999) <= T_REL
+    kinds = np.array([n[0] for n in desc.nodes])
+    assert (kinds[node[node >= 0]] == A.RL_RTC_TRIANGLE).mean() > 0.03  # triangles under Csgs are really seen
 
 
 def csg_stress_scene(w=320, h=200):
