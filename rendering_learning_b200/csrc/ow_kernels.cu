@@ -484,6 +484,59 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
 // runs for all parked lanes together once `leaf_min` of them wait (or nobody can step).  leaf_min = 32 degenerates to
 // the while-while schedule (v4).  ncu (profiles/r01_ncu_k_ow_render_v4.json, _v5.json): node steps run at 20 instead of 12.5
 // lanes, the whole kernel at 16 instead of 11.3.
+// ---- CTA-level reserve of work items ------------------------------------------------------------------------------------
+// Warps take their batches (<= 64 items) from a reserve the whole CTA shares; the reserve refills from the GLOBAL queue
+// with one atomic per `qbatch` items (512), the next refill prefetched one reserve ahead so that its round trip — over
+// NVLink when the counter is rank 0's — overlaps rendering.  Round 1 (and the first half of round 2) popped the global
+// counter once per WARP batch: 790 k same-address atomics per cover-scene step, 56 M/s at 8 GPUs, all landing on one L2
+// slice of GPU 0 — the ~1.7 ms per step that did not scale (14.0 ms at 8 GPUs against 12.3 ms = 98.5 / 8).
+struct ItemReserve {
+    volatile int it_lock, it_dry, nx_size;
+    volatile long long it_next, it_end;
+    volatile unsigned long long nx_base;  // prefetched next refill (its atomic was issued one refill ago)
+};
+__device__ __forceinline__ void reserve_init(ItemReserve& r, unsigned long long* queue, int sys_queue, int qbatch) {
+    r.it_lock = 0;
+    r.it_dry = 0;
+    r.it_next = r.it_end = 0;
+    r.nx_size = qbatch;
+    r.nx_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch) : atomicAdd(queue, (unsigned long long)qbatch);
+}
+// `n` work items for one service batch, out of the CTA's reserved batch of the global queue (one lane calls).  The next
+// batch's global atomic (system scope over NVLink when the counter is rank 0's) was issued when the current one was
+// installed, so its round trip overlaps a whole batch of rendering.  Returns how many were granted from *start on.
+__device__ __forceinline__ int items_take(ItemReserve& ctl, int n, long long n_items, unsigned long long* queue, int sys_queue, int qbatch,
+                                          int qtail, long long q_guided, long long* start, int* dry) {
+    while (atomicCAS((int*)&ctl.it_lock, 0, 1) != 0) __nanosleep(32);
+    __threadfence_block();
+    long long nx = ctl.it_next, en = ctl.it_end;
+    int isdry = ctl.it_dry;
+    if (nx >= en && !isdry) {
+        nx = (long long)ctl.nx_base;
+        const int got = ctl.nx_size;
+        en = nx + got < n_items ? nx + got : n_items;
+        if (nx >= n_items) {
+            isdry = 1;
+            en = nx;
+            ctl.it_dry = 1;
+        } else {
+            // guided self-scheduling: full batches while the queue is long, small ones near its end
+            const int want = n_items - nx > q_guided ? qbatch : qtail;
+            ctl.nx_size = want;
+            ctl.nx_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)want) : atomicAdd(queue, (unsigned long long)want);
+        }
+        ctl.it_end = en;
+    }
+    const long long avail = en - nx;
+    const int take = (long long)n < avail ? n : (int)avail;
+    *start = nx;
+    ctl.it_next = nx + take;
+    *dry = isdry;
+    __threadfence_block();
+    atomicExch((int*)&ctl.it_lock, 0);
+    return take;
+}
+
 // TRACE = true runs caller-supplied rays through the SAME loop (work items = ray indices, "service" = write the rl_hit of
 // the finished ray and load the next one): rl_trace_batch is this kernel, not a second traversal.
 struct TraceIO {
@@ -494,8 +547,8 @@ struct TraceIO {
 template <bool COUNT, int MINB, int PRIMS, bool TRACE = false, int OPT = 2>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
-                                                          int sys_queue, int qbatch, long long q_guided, int svc_min, int leaf_min,
-                                                          TraceIO tio) {
+                                                          int sys_queue, int qbatch, int wbatch, long long q_guided, int svc_min,
+                                                          int leaf_min, TraceIO tio) {
     LocalCount<COUNT> lc;
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -525,22 +578,19 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     unsigned ray_rnd = 0u;  // the ray's draw for ConstantMedium scattering distances
     OwHit hit;
     hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
-    // queue (warp-uniform, one slot per warp in shared memory): the current reserved batch [next, end) and the base of
-    // the prefetched next batch, whose atomic was issued one batch ago
+    // work items: each warp owns a batch [next, end) taken from the CTA's reserve (ItemReserve above), decoded into a table
     __shared__ long long sm_qnext[8], sm_qend[8], sm_qfirst[8];
-    __shared__ unsigned long long sm_qbase[8];
-    __shared__ int sm_qdry[8], sm_qsize[8];
-    constexpr int OW_ITEM_TABLE = 64;  // >= the largest batch a warp reserves (launch_ow_render clamps qbatch to 64)
+    __shared__ int sm_qdry[8];
+    __shared__ ItemReserve sm_reserve;
+    constexpr int OW_ITEM_TABLE = 64;  // the largest batch a warp takes
     __shared__ int sm_it_xy[8][OW_ITEM_TABLE], sm_it_chunk[8][OW_ITEM_TABLE], sm_it_s0[8][OW_ITEM_TABLE], sm_it_s1[8][OW_ITEM_TABLE];
     const int wid = threadIdx.x >> 5;
     if (lane == 0) {
         sm_qnext[wid] = sm_qend[wid] = sm_qfirst[wid] = 0;
         sm_qdry[wid] = 0;
-        sm_qsize[wid] = qbatch;
-        sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch)
-                                  : atomicAdd(queue, (unsigned long long)qbatch);
     }
-    __syncwarp();
+    if (threadIdx.x == 0) reserve_init(sm_reserve, queue, sys_queue, qbatch);
+    __syncthreads();
     while (true) {
         // ================= service: every lane that is not mid-traversal =================
         const bool svc = node == TRAV_END && !done;
@@ -593,22 +643,18 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             bool q_dry = sm_qdry[wid] != 0;
             __syncwarp();
             if (cur_next >= cur_end && !q_dry) {
-                cur_next = (long long)sm_qbase[wid];
-                const int got = sm_qsize[wid];
-                cur_end = cur_next + got < jt.n_items ? cur_next + got : jt.n_items;
-                __syncwarp();
-                if (cur_next >= jt.n_items) {
-                    q_dry = true;
-                    cur_end = cur_next;
-                } else if (lane == 0) {
-                    // guided self-scheduling: full batches while the queue is long, one item per lane near its end,
-                    // so the last warps to finish hold little work (the tail was 5-7 ms of a 25 ms 8-GPU step)
-                    const int want = jt.n_items - cur_next > q_guided ? qbatch : 32;
-                    sm_qsize[wid] = want;
-                    sm_qbase[wid] = sys_queue ? atomicAdd_system(queue, (unsigned long long)want)
-                                              : atomicAdd(queue, (unsigned long long)want);
-                    sm_qfirst[wid] = cur_next;
-                }
+                // guided self-scheduling lives in the reserve: full refills while the queue is long, small ones near its
+                // end, so the last CTAs to finish hold little work
+                long long start = 0;
+                int take = 0, dry = 0;
+                if (lane == 0) take = items_take(sm_reserve, wbatch, jt.n_items, queue, sys_queue, qbatch, qbatch < 128 ? qbatch : 128, q_guided, &start, &dry);
+                take = __shfl_sync(FULL, take, 0);
+                dry = __shfl_sync(FULL, dry, 0);
+                start = __shfl_sync(FULL, start, 0);
+                cur_next = start;
+                cur_end = start + take;
+                if (take == 0 && dry) q_dry = true;
+                if (lane == 0) sm_qfirst[wid] = cur_next;
                 // Decode the WHOLE batch now, with every lane: item -> (job, chunk, pixel, sample range) is ~300 instructions of
                 // 64-bit divisions and a binary search, and round 1 ran it per item at ~2 of 32 lanes — whenever a service
                 // round happened to include a lane that had just finished its item — for 8 % of all warp instructions
@@ -778,9 +824,7 @@ __host__ __device__ constexpr size_t smem_bytes(int prims, int P) {
 struct Ctl {
     volatile unsigned r_head, r_tail, d_head, d_tail;  // READY / DONE rings
     volatile int live, abort;                         // slots not yet dead; watchdog
-    volatile int it_lock, it_dry, nx_size;            // CTA-level item batch (reserved from the global queue)
-    volatile long long it_next, it_end;
-    volatile unsigned long long nx_base;              // prefetched next batch (its atomic was issued one batch ago)
+    ItemReserve items;                                // CTA-level item reserve (refilled from the global queue)
 };
 
 using rl::TraceIO;
@@ -833,40 +877,6 @@ __device__ __forceinline__ int ring_pop(int* ring, volatile unsigned* head, vola
     return id;
 }
 
-// `n` work items for one service batch, out of the CTA's reserved batch of the global queue (one lane calls).  The next
-// batch's global atomic (system scope over NVLink when the counter is rank 0's) was issued when the current one was
-// installed, so its round trip overlaps a whole batch of rendering.  Returns how many were granted from *start on.
-__device__ __forceinline__ int items_take(Ctl& ctl, int n, long long n_items, unsigned long long* queue, int sys_queue, int qbatch,
-                                          long long q_guided, long long* start, int* dry) {
-    while (atomicCAS((int*)&ctl.it_lock, 0, 1) != 0) __nanosleep(32);
-    __threadfence_block();
-    long long nx = ctl.it_next, en = ctl.it_end;
-    int isdry = ctl.it_dry;
-    if (nx >= en && !isdry) {
-        nx = (long long)ctl.nx_base;
-        const int got = ctl.nx_size;
-        en = nx + got < n_items ? nx + got : n_items;
-        if (nx >= n_items) {
-            isdry = 1;
-            en = nx;
-            ctl.it_dry = 1;
-        } else {
-            // guided self-scheduling: full batches while the queue is long, small ones near its end
-            const int want = n_items - nx > q_guided ? qbatch : 32;
-            ctl.nx_size = want;
-            ctl.nx_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)want) : atomicAdd(queue, (unsigned long long)want);
-        }
-        ctl.it_end = en;
-    }
-    const long long avail = en - nx;
-    const int take = (long long)n < avail ? n : (int)avail;
-    *start = nx;
-    ctl.it_next = nx + take;
-    *dry = isdry;
-    __threadfence_block();
-    atomicExch((int*)&ctl.it_lock, 0);
-    return take;
-}
 }  // namespace v6
 
 template <bool COUNT, int MINB, int PRIMS, int MODE>
@@ -907,11 +917,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
         ctl.d_tail = (unsigned)P;
         ctl.live = P;
         ctl.abort = 0;
-        ctl.it_lock = 0;
-        ctl.it_dry = 0;
-        ctl.it_next = ctl.it_end = 0;
-        ctl.nx_size = qbatch;
-        ctl.nx_base = sys_queue ? atomicAdd_system(queue, (unsigned long long)qbatch) : atomicAdd(queue, (unsigned long long)qbatch);
+        reserve_init(ctl.items, queue, sys_queue, qbatch);
     }
     __syncthreads();
 
@@ -1052,7 +1058,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
                 long long start = 0;
                 int take = 0, dry = 0;
                 if ((int)lane == leader)
-                    take = items_take(ctl, __popc(m_need), n_items, queue, sys_queue, qbatch, q_guided, &start, &dry);
+                    take = items_take(ctl.items, __popc(m_need), n_items, queue, sys_queue, qbatch, 32, q_guided, &start, &dry);
                 take = __shfl_sync(FULL, take, leader);
                 dry = __shfl_sync(FULL, dry, leader);
                 start = __shfl_sync(FULL, start, leader);
@@ -1306,7 +1312,7 @@ static OwCam make_cam(const rl_ow_camera* p, uint32_t first_sample) {
 
 namespace {
 constexpr int PRIMS_FLAT = PRIMS_TRIS | PRIMS_QUADS;
-typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int, TraceIO);
+typedef void (*K5)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, int, long long, int, int, TraceIO);
 typedef void (*K6)(DevScene, OwCam, JobTable, float*, unsigned long long*, Counters*, int, int, long long, int, int, int, int,
                    TraceIO);
 
@@ -1363,13 +1369,16 @@ cudaError_t launch_k5(K5 k5, int prims, const DevScene& sc, const OwCam& c, cons
     long long grid = (long long)sm_count * per_sm;  // persistent: every SM full, a multiple of the SM count
     if (grid > want && !shared_queue) grid = want;
     if (grid < 1) grid = 1;
-    // items a warp reserves per atomic: 64 when there is plenty of work, never so many that warps starve
+    // a warp takes up to 64 items at a time from its CTA's reserve; the reserve refills from the global queue 512 at a
+    // time (ONE atomic on the global counter per 512 items), never so many that CTAs starve; below `q_guided` remaining
+    // items the refills shrink to one warp batch (a shared queue feeds up to 8 GPUs)
     long long per_warp = jt.n_items / (grid * 8 * 4);
-    int qbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
-    // below this many remaining items a warp reserves 32 instead of qbatch (a shared queue feeds up to 8 GPUs)
-    const long long q_guided = grid * 8 * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
-    k5<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, shared_queue ? 1 : 0, qbatch, q_guided, svc_min,
-                                           leaf_min, tio);
+    const int wbatch = (int)(per_warp < 32 ? 32 : (per_warp > 64 ? 64 : per_warp));
+    long long per_cta = jt.n_items / (grid * 4);
+    const int qbatch = (int)(per_cta < wbatch ? wbatch : (per_cta > 512 ? 512 : per_cta));
+    const long long q_guided = grid * (long long)qbatch * 2 * (shared_queue ? 8 : 1);
+    k5<<<(unsigned)grid, 256, 0, stream>>>(sc, c, jt, d_partial, d_queue, d_counters, shared_queue ? 1 : 0, qbatch, wbatch, q_guided,
+                                           svc_min, leaf_min, tio);
     return cudaGetLastError();
 }
 
