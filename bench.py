@@ -247,6 +247,11 @@ class OwBench:
             self.partial = torch.zeros((self.nc, self.H, self.W, 4), dtype=torch.float32, device=dev)
         self.shared = world_size > 1 and rd.setup_shared_queue(ctx, self.partial_bytes if self.mgpu == "fused" else 0)
         self.last_slot = None
+        # diagnostics: CUDA events around this rank's render KERNEL alone inside a multi-GPU step
+        self.kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if world_size > 1 else None
+
+    def kernel_only_ms(self):
+        return self.kev[0].elapsed_time(self.kev[1]) if self.kev else None
 
     def instrumented(self):
         import torch
@@ -266,9 +271,9 @@ class OwBench:
             self.ctx.ow_reduce_device(self.cam, self.partial.data_ptr(), self.frame.data_ptr(), self.stream)
             return 2
         if self.mgpu == "fused":
-            self.last_slot = self.rd.render_ow_fused(self.ctx, self.cam, 0, self.frame, self.nc, self.H, self.W)
+            self.last_slot = self.rd.render_ow_fused(self.ctx, self.cam, 0, self.frame, self.nc, self.H, self.W, events=self.kev)
             return 2 if self.rank == 0 else 1
-        self.rd.render_ow_shared_queue(self.ctx, self.cam, 0, self.partial, self.frame, self.nc, self.H, self.W)
+        self.rd.render_ow_shared_queue(self.ctx, self.cam, 0, self.partial, self.frame, self.nc, self.H, self.W, events=self.kev)
         return 2 if self.rank == 0 else 1
 
     def check(self):
@@ -415,6 +420,9 @@ def main():
         ctx.synchronize()
         b.check()
         ms = max_over_ranks(e0.elapsed_time(e1)) / n_steps
+        if getattr(b, "kev", None) is not None:  # the last step's kernel alone, slowest and fastest rank
+            k = b.kernel_only_ms()
+            b.kernel_only = {"max_ms": max_over_ranks(k), "min_ms": -max_over_ranks(-k)}
         return ms, int(reduce_ranks(float(launches), dist.ReduceOp.SUM)), wall
 
     B = OwBench(ctx, wl, args.spp, world_size, rank, dev) if wl["kind"] == "ow" else RtcBench(ctx, wl, world_size, rank, dev)
@@ -537,7 +545,7 @@ def main():
             "config": {"workload": wl["name"], "image": [B.W, B.H], "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": B.parallelism()},
             "samples_per_s": B.samples / (ms_per_step * 1e-3), "rays_per_step": rays, "samples_per_step": B.samples,
-            "wall_s_timed_region": t_wall, "frame_md5": frame_md5,
+            "wall_s_timed_region": t_wall, "frame_md5": frame_md5, "kernel_only_last_step": getattr(B, "kernel_only", None),
             "clocks": clocks, "gpu_launches": total_launches,
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(B.desc.nbytes()),
                     "d2h_bytes_per_step": int(B.out_bytes), "ms_per_step": e2e_s * 1e3, "steps": e2e_n,

@@ -140,7 +140,7 @@ def setup_shared_queue(ctx, partial_bytes: int = 0) -> bool:
 _fused_state = {"render": 0}
 
 
-def render_ow_fused(ctx, cam, first_sample: int, out, n_chunks: int, height: int, width: int):
+def render_ow_fused(ctx, cam, first_sample: int, out, n_chunks: int, height: int, width: int, events=None):
     """OW render, fully device-driven: every GPU's persistent warps pop items from rank 0's counter and store the
     finished partial sums straight into rank 0's buffer, both over NVLink peer memory.
 
@@ -157,7 +157,11 @@ def render_ow_fused(ctx, cam, first_sample: int, out, n_chunks: int, height: int
     jobs = [(0, 0, width, height, 0, n_chunks)]
     if rank == 0:
         ctx.queue_reset(stream, slot ^ 1)
+    if events:
+        events[0].record()
     ctx.render_ow_shared(cam, first_sample, jobs, 0, stream, slot)
+    if events:
+        events[1].record()
     dist.all_reduce(_token(out.device))  # every rank's kernel has finished: its stores have landed in rank 0's HBM
     if rank == 0:
         ctx.ow_reduce_shared(cam, slot, out.data_ptr(), stream)
@@ -174,7 +178,7 @@ def check_fused_complete(ctx, cam, slot: int, n_chunks: int, height: int, width:
         raise RuntimeError(f"multi-GPU render incomplete: {got} of {want} work items were stored")
 
 
-def render_ow_shared_queue(ctx, cam, first_sample: int, partial, out, n_chunks: int, height: int, width: int):
+def render_ow_shared_queue(ctx, cam, first_sample: int, partial, out, n_chunks: int, height: int, width: int, events=None):
     """OW render with the cross-GPU device queue: one persistent launch per GPU, warps of every GPU pop
     (pixel x sample-chunk) items from rank 0's counter over NVLink; NCCL sum-gathers the partial sums (the comparison
     point for the fused gather above)."""
@@ -187,7 +191,11 @@ def render_ow_shared_queue(ctx, cam, first_sample: int, partial, out, n_chunks: 
     partial.zero_()
     if rank == 0:
         ctx.queue_reset(stream, slot ^ 1)
+    if events:
+        events[0].record()
     ctx.render_ow_shared(cam, first_sample, [(0, 0, width, height, 0, n_chunks)], partial.data_ptr(), stream, slot)
+    if events:
+        events[1].record()
     dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM)
     if rank == 0:
         ctx.ow_reduce_device(cam, partial.data_ptr(), out.data_ptr(), stream)
@@ -235,10 +243,16 @@ def camera_render_ow(camera, world, ctx, buffers):
     rank, world_size = _rank_world()
     sd = world if isinstance(world, SceneDesc) else ow.lower_world(world)
     ctx.scene_upload(sd)
-    slot = render_ow_fused(ctx, camera.params.abi(), 0, buffers.frame, buffers.nc, buffers.H, buffers.W)
-    if rank != 0:
-        return None
-    check_fused_complete(ctx, camera.params.abi(), slot, buffers.nc, buffers.H, buffers.W)
+    if getattr(buffers, "partial", None) is not None:  # the NCCL sum-gather comparison mode keeps its own partial buffer
+        render_ow_shared_queue(ctx, camera.params.abi(), 0, buffers.partial, buffers.frame, buffers.nc, buffers.H, buffers.W)
+        if rank != 0:
+            return None
+        ctx.synchronize()
+    else:
+        slot = render_ow_fused(ctx, camera.params.abi(), 0, buffers.frame, buffers.nc, buffers.H, buffers.W)
+        if rank != 0:
+            return None
+        check_fused_complete(ctx, camera.params.abi(), slot, buffers.nc, buffers.H, buffers.W)
     sums = buffers.frame.cpu().numpy()  # pageable
     return ow.Canvas(camera.params.samples_per_pixel, buffers.W, buffers.H, sums.astype("float64"))
 
