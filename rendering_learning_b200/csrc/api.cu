@@ -64,6 +64,7 @@ struct rl_ctx {
     int upload_launches = 0;
     // work buffers
     DevBuf counters, queue, jobs, prefix, frame, frame8, partial, rays, hits;
+    DevBuf wf_state, wf_rays, wf_ctr;  // the global-wavefront variant's path state (ow.variant = 7)
     ObjMesh mesh;                  // the mesh rl_obj_parse left on this device (RL_RTC_MESH / RL_OW_MESH nodes instance it)
     rl_obj_info mesh_info{};
     bool has_mesh = false;
@@ -211,7 +212,8 @@ void rl_destroy(rl_ctx* c) {
                      &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
-                     &c->jobs, &c->prefix, &c->frame, &c->frame8, &c->partial, &c->rays, &c->hits, &c->self_refs};
+                     &c->jobs, &c->prefix, &c->frame, &c->frame8, &c->partial, &c->rays, &c->hits, &c->self_refs,
+                     &c->wf_state, &c->wf_rays, &c->wf_ctr};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : c->image_texels) b.release();
     for (DevBuf& b : c->job_tables) b.release();
@@ -299,7 +301,7 @@ int rl_synchronize(rl_ctx* c) {
 }
 
 static const struct { const char* name; int OwTuning::*field; int lo, hi; } k_options[] = {
-    {"ow.variant", &OwTuning::variant, 5, 6},        {"ow.slots", &OwTuning::slots, 0, 512},
+    {"ow.variant", &OwTuning::variant, 5, 7},        {"ow.slots", &OwTuning::slots, 0, 1 << 22},
     {"ow.minb", &OwTuning::minb, 0, 4},              {"ow.ctas_per_sm", &OwTuning::ctas_per_sm, 0, 8},
     {"ow.svc_lo", &OwTuning::svc_lo, 0, 32},         {"ow.exit_min", &OwTuning::exit_min, 0, 32},
     {"ow.leaf_min", &OwTuning::leaf_min, 0, 32},     {"ow.svc_min", &OwTuning::svc_min, 0, 32},
@@ -836,9 +838,23 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
         return RL_OK;
     }
     CK(c, reset_stats(c, s));
-    CK(c, cudaEventRecord(c->ev0, s));
-    CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
-                           c->counters.as<Counters>(), c->instrumented, c->sm_count, s, false, c->tune));
+    int wf_launches = 0;
+    if (c->tune.variant == 7) {  // the global-wavefront A/B variant: path state in global memory
+        int S = c->tune.slots >= 1024 ? c->tune.slots : (1 << 19);
+        S = (S + 255) / 256 * 256;
+        CK(c, c->wf_state.reserve(sizeof(float) * (size_t)OW_WF_WORDS * S));
+        CK(c, c->wf_rays.reserve(sizeof(int) * (size_t)S));
+        CK(c, c->wf_ctr.reserve(256));
+        WavefrontBuffers wb{c->wf_state.as<float>(), c->wf_rays.as<int>(), c->wf_ctr.p, S};
+        CK(c, cudaMemsetAsync(c->queue.p, 0, 2 * sizeof(unsigned long long), s));
+        CK(c, cudaEventRecord(c->ev0, s));
+        CK(c, launch_ow_wavefront(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
+                                  c->counters.as<Counters>(), wb, c->sm_count, s, c->tune, &wf_launches));
+    } else {
+        CK(c, cudaEventRecord(c->ev0, s));
+        CK(c, launch_ow_render(c->ds, cam, first_sample, jt, (float*)d_partial, c->queue.as<unsigned long long>(),
+                               c->counters.as<Counters>(), c->instrumented, c->sm_count, s, false, c->tune));
+    }
     CK(c, cudaEventRecord(c->ev1, s));
     rl_stats st{};
     rc = read_counters(c, s, &st);
@@ -846,7 +862,7 @@ int rl_render_ow_device(rl_ctx* c, const rl_ow_camera* cam, uint32_t first_sampl
     CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     st.kernel_ms = ms;
     st.upload_ms = c->upload_ms;
-    st.kernel_launches = jt.n_items > 0 ? 1 : 0;
+    st.kernel_launches = wf_launches ? wf_launches : (jt.n_items > 0 ? 1 : 0);
     uint64_t samples = 0;
     for (int i = 0; i < n_jobs; i++) {
         uint64_t px = (uint64_t)(jobs[i].x1 - jobs[i].x0) * (uint64_t)(jobs[i].y1 - jobs[i].y0);

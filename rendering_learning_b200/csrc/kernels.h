@@ -35,7 +35,8 @@ __host__ __device__ inline void ow_chunk_range(int spp, int n_chunks, int chunk,
 // WHEN work is done, never what is computed: the image is bit-identical for every setting (tests/test_gpu_ow.py).
 struct OwTuning {
     int variant = 5;      // 5: per-lane paths, service rounds inside the warp (production); 6: CTA-pooled paths (the measured
-                          // shared-memory wavefront experiment, 1.6-1.9x slower: DESIGN.md §4)
+                          // shared-memory wavefront experiment, 1.6-1.9x slower: DESIGN.md §4); 7: the GLOBAL wavefront
+                          // (path state in L2 / HBM, one logic + one trace kernel per bounce: the other measured A/B)
     int slots = 0;        // v6: path slots per CTA (256 .. 512)
     int minb = 0;         // resident CTAs per SM the kernel is compiled for (3 or 4)
     int ctas_per_sm = 0;  // launch fewer CTAs per SM than fit
@@ -49,6 +50,17 @@ int ow_image_height(const rl_ow_camera* c);
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
                              float* d_partial, unsigned long long* d_queue, Counters* d_counters, bool instrumented,
                              int sm_count, cudaStream_t stream, bool shared_queue, const OwTuning& tune);
+// global-wavefront variant (ow.variant = 7): state [wf words][slots] f32, ray list [slots] i32, a small counter block
+struct WavefrontBuffers {
+    float* state;
+    int* ray_list;
+    void* ctr;
+    int slots;
+};
+constexpr int OW_WF_WORDS = 25;
+cudaError_t launch_ow_wavefront(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
+                                float* d_partial, unsigned long long* d_queue, Counters* d_counters, const WavefrontBuffers& wb,
+                                int sm_count, cudaStream_t stream, const OwTuning& tune, int* launches);
 cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream);
 // 8-bit output encoders (RTC/src/draw/canvas.rs:53-56; OW/src/color.rs:47-57, 130-136), n = W*H*3 channels
 cudaError_t launch_encode_rtc_u8(const float* d_rgb, uint8_t* d_out, size_t n, cudaStream_t stream);

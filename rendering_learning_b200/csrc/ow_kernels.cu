@@ -1206,6 +1206,279 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
     lc.flush(counters);
 }
 
+// ---- v7: GLOBAL wavefront — the design north_star names, built once for the measured A/B ----------------
+// Path state lives in global memory (SoA, [word][slot], S slots), the render alternates two kernels:
+//   k_wf_logic  one thread per slot: hit record + emitted + scatter of the ray that came back, retire / refill the item,
+//               regenerate the camera ray, big-list test; the slots that have a ray to trace are compacted into
+//               `ray_list` (ballot / popc inside the warp, one shared-memory and one global atomic per CTA);
+//   k_wf_trace  persistent warps: lanes fetch slot ids from `ray_list` dynamically (warp-aggregated atomic), run the SAME
+//               node steps / leaf rounds as the production kernel, write the hit into the slot and fetch again.
+// Per-path arithmetic, RNG counters and the order samples are folded in are the production kernel's, so the frame is
+// bit-identical; what differs is where the state lives (L2 / HBM instead of registers + shared memory) and that every
+// stage starts with full warps.
+namespace wf {
+enum { OX, OY, OZ, DX, DY, DZ, TIME, SELF, HT, HREF, THRX, THRY, THRZ, DEPTH, XY, S, SEND, CHUNK, ACCX, ACCY, ACCZ, FLAGS, HB1, HB2, RND, N_WORDS };
+static_assert(N_WORDS == OW_WF_WORDS, "kernels.h sizes the state buffer");
+struct Ctr {
+    unsigned long long items;     // next work item
+    unsigned long long retired;   // items finished (completion accounting)
+    unsigned ray_count[2];        // rays to trace, ping-pong by iteration parity
+    unsigned fetch;               // next ray_list entry the trace kernel hands out
+    unsigned live;                // slots that are not dead yet
+};
+}  // namespace wf
+
+template <int PRIMS>
+__global__ void __launch_bounds__(256) k_wf_logic(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial, float* __restrict__ st,
+                                                  int* __restrict__ ray_list, wf::Ctr* __restrict__ ctr, Counters* counters,
+                                                  int n_slots, int iter) {
+    using namespace wf;
+    constexpr bool HAS_B = (PRIMS & (PRIMS_TRIS | PRIMS_QUADS | PRIMS_MEDIA)) != 0;
+    LocalCount<false> lc;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t NS = (size_t)n_slots;
+    int* sti = reinterpret_cast<int*>(st);
+#define WS(w) st[(size_t)(w) * NS + id]
+#define WI(w) sti[(size_t)(w) * NS + id]
+    const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
+    const int par = iter & 1;
+    if (id == 0) {  // nobody touches these during this kernel
+        ctr->fetch = 0u;
+        ctr->ray_count[par ^ 1] = 0u;
+    }
+    __shared__ int sm_need[8], sm_emit[8];
+    __shared__ long long sm_item_base;
+    __shared__ unsigned sm_ray_base;
+    const bool valid = id < n_slots;
+    int flags = valid ? WI(FLAGS) : 2;
+    bool alive = (flags & 1) != 0, dead = (flags & 2) != 0;
+    bool has_item = valid && !dead && WI(CHUNK) >= 0;
+    int s = 0, s_end = 0, xy = 0;
+    unsigned pixel = 0;
+    Path p;
+    p.depth = 0;
+    if (has_item) {
+        s = WI(S);
+        s_end = WI(SEND);
+        xy = WI(XY);
+        pixel = (unsigned)((xy >> 16) * cam.width + (xy & 0xffff));
+    }
+    if (alive) {  // its ray came back from the trace kernel
+        p.o = f3(WS(OX), WS(OY), WS(OZ));
+        p.d = f3(WS(DX), WS(DY), WS(DZ));
+        p.time = WS(TIME);
+        p.self_ref = WI(SELF);
+        p.thr = f3(WS(THRX), WS(THRY), WS(THRZ));
+        p.depth = WI(DEPTH);
+        OwHit h;
+        h.t = WS(HT);
+        h.ref = WI(HREF);
+        h.b1 = HAS_B ? WS(HB1) : 0.0f;
+        h.b2 = HAS_B ? WS(HB2) : 0.0f;
+        const unsigned bounce = (unsigned)(cam.max_depth - p.depth + 1);
+        const uint4 rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), bounce, 0u), key);
+        float3 rad;
+        if (!ow_shade<false, PRIMS>(sc, cam, p, h, rnd, rad, lc)) {
+            WS(ACCX) += rad.x;
+            WS(ACCY) += rad.y;
+            WS(ACCZ) += rad.z;
+            alive = false;
+            s++;
+        }
+    }
+    unsigned retired = 0;
+    if (has_item && !alive && s == s_end) {
+        const size_t idx = ((size_t)WI(CHUNK) * cam.height + (xy >> 16)) * cam.width + (xy & 0xffff);
+        reinterpret_cast<float4*>(partial)[idx] = make_float4(WS(ACCX), WS(ACCY), WS(ACCZ), 0.0f);
+        has_item = false;
+        retired++;
+    }
+    // ---- work items: one global atomic per CTA ----
+    const bool need = valid && !dead && !has_item;
+    const unsigned m_need = __ballot_sync(FULL, need);
+    if (lane == 0) sm_need[wid] = __popc(m_need);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { int c = sm_need[w]; sm_need[w] = tot; tot += c; }
+        sm_item_base = tot ? (long long)atomicAdd(&ctr->items, (unsigned long long)tot) : 0ll;
+    }
+    __syncthreads();
+    if (need) {
+        const long long item = sm_item_base + sm_need[wid] + __popc(m_need & ((1u << lane) - 1u));
+        if (item < jt.n_items) {
+            const int j = find_job(jt, item);
+            const rl_job job = jt_job(jt, j);
+            const long long local = item - jt_prefix(jt, j);
+            const int w = job.x1 - job.x0, hgt = job.y1 - job.y0;
+            const long long pp = padded_pixels(w, hgt);
+            const int ck = (int)(local / pp);
+            int px, py;
+            tile_pixel(w, hgt, local - (long long)ck * pp, &px, &py);
+            if (px < w && py < hgt) {
+                const int x = job.x0 + px, y = job.y0 + py, chunk = job.chunk_begin + ck;
+                ow_chunk_range(cam.spp, cam.n_chunks, chunk, &s, &s_end);
+                if (cam.max_depth <= 0) s = s_end;
+                xy = (y << 16) | x;
+                pixel = (unsigned)(y * cam.width + x);
+                WI(XY) = xy;
+                WI(SEND) = s_end;
+                WI(CHUNK) = chunk;
+                WS(ACCX) = WS(ACCY) = WS(ACCZ) = 0.0f;
+                has_item = true;
+            } else {
+                retired++;  // a padded slot: a work item with nothing to render; the slot asks again next iteration
+            }
+        } else {
+            dead = true;  // the queue is dry
+        }
+        if (!has_item) WI(CHUNK) = -1;
+    }
+    if (has_item && !alive && s < s_end) {
+        ow_camera_ray(cam, xy & 0xffff, xy >> 16, (unsigned)(cam.first_sample + s), p);
+        alive = true;
+    }
+    if (alive) {
+        p.d = p.d * rsqrtf(dot(p.d, p.d));
+        const float tm = fmaf(1e-5f, max_abs(p.o), 1e-6f);
+        TriShear sh;
+        sh.k = 0; sh.Sx = sh.Sy = sh.Sz = 0.0f;
+        if (PRIMS & PRIMS_TRIS) sh = make_shear(p.o, p.d);
+        unsigned rr = 0u;
+        if (PRIMS & PRIMS_MEDIA)
+            rr = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
+        OwHit h0;
+        h0.t = RL_INF; h0.ref = -1; h0.b1 = h0.b2 = 0.0f;
+        for (int k = 0; k < sc.n_big; k++)
+            ow_leaf_test_od<false, PRIMS>(sc, sc.big_refs[k], p.o, p.d, sh, p.time, p.self_ref, tm, h0, lc, rr);
+        WS(OX) = p.o.x; WS(OY) = p.o.y; WS(OZ) = p.o.z;
+        WS(DX) = p.d.x; WS(DY) = p.d.y; WS(DZ) = p.d.z;
+        WS(TIME) = p.time;
+        WI(SELF) = p.self_ref;
+        WS(THRX) = p.thr.x; WS(THRY) = p.thr.y; WS(THRZ) = p.thr.z;
+        WI(DEPTH) = p.depth;
+        WS(HT) = h0.t;
+        WI(HREF) = h0.ref;
+        if (HAS_B) { WS(HB1) = h0.b1; WS(HB2) = h0.b2; }
+        if (PRIMS & PRIMS_MEDIA) WI(RND) = (int)rr;
+    }
+    if (valid) {
+        WI(S) = s;
+        WI(FLAGS) = (alive ? 1 : 0) | (dead ? 2 : 0);
+    }
+    // ---- compaction of the slots that have a ray: ballot / popc, one shared and one global atomic per CTA ----
+    const unsigned m_emit = __ballot_sync(FULL, alive);
+    if (lane == 0) sm_emit[wid] = __popc(m_emit);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { int c = sm_emit[w]; sm_emit[w] = tot; tot += c; }
+        sm_ray_base = tot ? atomicAdd(&ctr->ray_count[par], (unsigned)tot) : 0u;
+    }
+    __syncthreads();
+    if (alive) ray_list[sm_ray_base + sm_emit[wid] + __popc(m_emit & ((1u << lane) - 1u))] = id;
+    for (int off = 16; off > 0; off >>= 1) retired += __shfl_xor_sync(FULL, retired, off);
+    if (lane == 0 && retired) atomicAdd(&ctr->retired, (unsigned long long)retired);
+    lc.flush(counters);
+#undef WS
+#undef WI
+}
+
+template <int PRIMS>
+__global__ void __launch_bounds__(256, 4) k_wf_trace(DevScene sc, float* __restrict__ st, const int* __restrict__ ray_list,
+                                                     wf::Ctr* __restrict__ ctr, Counters* counters, int n_slots, int iter,
+                                                     int exit_min, int leaf_min) {
+    using namespace wf;
+    constexpr bool HAS_B = (PRIMS & (PRIMS_TRIS | PRIMS_QUADS | PRIMS_MEDIA)) != 0;
+    LocalCount<false> lc;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const size_t NS = (size_t)n_slots;
+    int* sti = reinterpret_cast<int*>(st);
+    __shared__ int sm_stack[STACK_SM * 256];
+    TravStack stk;
+    stack_init<256>(stk, sm_stack + threadIdx.x);
+    StackSpill spill;
+    const unsigned n_rays = ctr->ray_count[iter & 1];
+    int slot = -1, node = TRAV_END;
+    float3 o = f3(0.0f, 0.0f, 0.0f), d = f3(0.0f, 0.0f, 1.0f), inv_d = f3(1.0f, 1.0f, 1.0f), oi = f3(0.0f, 0.0f, 0.0f);
+    float tmin = 0.0f, time = 0.0f;
+    int self_ref = -1;
+    TriShear shear;
+    shear.k = 0; shear.Sx = shear.Sy = shear.Sz = 0.0f;
+    unsigned ray_rnd = 0u;
+    OwHit hit;
+    hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
+    bool dry = false;
+    while (true) {
+        // lanes whose ray is finished: hit into the slot
+        if (slot >= 0 && node == TRAV_END) {
+            st[(size_t)HT * NS + slot] = hit.t;
+            sti[(size_t)HREF * NS + slot] = hit.ref;
+            if (HAS_B) {
+                st[(size_t)HB1 * NS + slot] = hit.b1;
+                st[(size_t)HB2 * NS + slot] = hit.b2;
+            }
+            slot = -1;
+        }
+        // idle lanes fetch the next ray (warp-aggregated)
+        const unsigned m_idle = __ballot_sync(FULL, slot < 0);
+        if (m_idle && !dry) {
+            const int want = __popc(m_idle), leader = __ffs(m_idle) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(&ctr->fetch, (unsigned)want);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (unsigned)want >= n_rays) dry = true;  // warp-uniform: nothing (more) beyond this batch
+            if (slot < 0) {
+                const unsigned k = base + (unsigned)__popc(m_idle & ((1u << lane) - 1u));
+                if (k < n_rays) {
+                    slot = ray_list[k];
+                    o = f3(st[(size_t)OX * NS + slot], st[(size_t)OY * NS + slot], st[(size_t)OZ * NS + slot]);
+                    d = f3(st[(size_t)DX * NS + slot], st[(size_t)DY * NS + slot], st[(size_t)DZ * NS + slot]);
+                    time = st[(size_t)TIME * NS + slot];
+                    self_ref = sti[(size_t)SELF * NS + slot];
+                    hit.t = st[(size_t)HT * NS + slot];
+                    hit.ref = sti[(size_t)HREF * NS + slot];
+                    if (HAS_B) {
+                        hit.b1 = st[(size_t)HB1 * NS + slot];
+                        hit.b2 = st[(size_t)HB2 * NS + slot];
+                    }
+                    if (PRIMS & PRIMS_MEDIA) ray_rnd = (unsigned)sti[(size_t)RND * NS + slot];
+                    inv_d = safe_inv_fast(d);
+                    oi = o * inv_d;
+                    tmin = fmaf(1e-5f, max_abs(o), 1e-6f);
+                    if (PRIMS & PRIMS_TRIS) shear = make_shear(o, d);
+                    stack_reset(stk);
+                    node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
+                }
+            }
+        }
+        const int n_act = __popc(__ballot_sync(FULL, slot >= 0));
+        if (n_act == 0) break;  // dry and nothing in flight
+        const int n_idle0 = 32 - n_act;
+        while (true) {
+            if (node < 0 && node != TRAV_END) {
+                ow_leaf_test_od<false, PRIMS>(sc, ~node, o, d, shear, time, self_ref, tmin, hit, lc, ray_rnd);
+                node = stack_pop<256>(stk, spill);
+            }
+            const int n_end = __popc(__ballot_sync(FULL, node == TRAV_END));
+            if (n_end == 32 || (!dry && n_end - n_idle0 >= exit_min)) break;
+            const int keep = 32 - n_end - leaf_min;
+            int n_in;
+            do {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    if (node >= 0) bvh2_step<false, 256>(sc.nodes, node, stk, spill, inv_d, oi, tmin, hit.t, lc, sc.n_bvh_nodes);
+                }
+                n_in = __popc(__ballot_sync(FULL, node >= 0));
+            } while (n_in > keep && n_in > 0);
+        }
+    }
+    lc.flush(counters);
+}
+
 // fold the per-chunk partial sums ([chunk][pixel] float4) in chunk order into [pixel][3]
 __global__ void k_ow_reduce(const float4* __restrict__ partial, float* __restrict__ out, size_t n_pixels, int n_chunks) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1434,6 +1707,57 @@ cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32
                          sm_count, stream, shared_queue, tune, tio);
     return launch_k5(pick_k5<false>(prims, minb, instrumented), prims, sc, c, jt, d_partial, d_queue, d_counters, sm_count, stream,
                      shared_queue, tune, tio);
+}
+
+// The global-wavefront render (ow.variant = 7, single GPU): alternate k_wf_logic / k_wf_trace until no slot has a ray left
+// and the item queue is dry; the host looks at the counters every 16 iterations.
+cudaError_t launch_ow_wavefront(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,
+                                float* d_partial, unsigned long long* d_queue, Counters* d_counters, const WavefrontBuffers& wb,
+                                int sm_count, cudaStream_t stream, const OwTuning& tune, int* launches) {
+    using namespace wf;
+    if (jt.n_items <= 0) return cudaSuccess;
+    const OwCam c = make_cam(cam, first_sample);
+    const int prims = scene_prims(sc);
+    const int S = wb.slots;
+    Ctr* ctr = reinterpret_cast<Ctr*>(wb.ctr);
+    cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(Ctr), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(wb.state + (size_t)FLAGS * S, 0, sizeof(float) * (size_t)S, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(wb.state + (size_t)CHUNK * S, 0xFF, sizeof(float) * (size_t)S, stream);  // -1: no item
+    if (e != cudaSuccess) return e;
+    typedef void (*KL)(DevScene, OwCam, JobTable, float*, float*, int*, Ctr*, Counters*, int, int);
+    typedef void (*KT)(DevScene, float*, const int*, Ctr*, Counters*, int, int, int, int);
+    KL kl;
+    KT kt;
+    switch (prims) {
+        case PRIMS_SPHERES: kl = k_wf_logic<PRIMS_SPHERES>; kt = k_wf_trace<PRIMS_SPHERES>; break;
+        case PRIMS_FLAT: kl = k_wf_logic<PRIMS_FLAT>; kt = k_wf_trace<PRIMS_FLAT>; break;
+        case PRIMS_ALL: kl = k_wf_logic<PRIMS_ALL>; kt = k_wf_trace<PRIMS_ALL>; break;
+        default: kl = k_wf_logic<PRIMS_FULL>; kt = k_wf_trace<PRIMS_FULL>; break;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const unsigned tgrid = (unsigned)(sm_count * per_sm), lgrid = (unsigned)((S + 255) / 256);
+    const int exit_min = tune.exit_min > 0 ? tune.exit_min : 8;
+    const int leaf_min = tune.leaf_min > 0 ? tune.leaf_min : 8;
+    int iter = 0, n_launch = 0;
+    for (;;) {
+        for (int k = 0; k < 16; k++, iter++) {
+            kl<<<lgrid, 256, 0, stream>>>(sc, c, jt, d_partial, wb.state, wb.ray_list, ctr, d_counters, S, iter);
+            kt<<<tgrid, 256, 0, stream>>>(sc, wb.state, wb.ray_list, ctr, d_counters, S, iter, exit_min, leaf_min);
+            n_launch += 2;
+        }
+        Ctr h;
+        e = cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        if (h.ray_count[(iter - 1) & 1] == 0u && (long long)h.items >= jt.n_items) break;
+        if (iter > (1 << 22)) return cudaErrorLaunchTimeout;  // cannot happen: every iteration retires rays
+    }
+    e = cudaMemcpyAsync(d_queue + 1, &ctr->retired, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);  // completion accounting
+    if (launches) *launches = n_launch;
+    return e == cudaSuccess ? cudaGetLastError() : e;
 }
 
 cudaError_t launch_ow_reduce(const rl_ow_camera* cam, const float* d_partial, float* d_out, cudaStream_t stream) {

@@ -4,8 +4,9 @@
   work queue, service / refill rounds, big list at ray start, unit directions, the scale-aware t_min, the
   start-on-surface rule, node steps, leaf rounds), so the hit-id checks below exercise the loop that renders — on the
   reference's own rays at bounce 0, 1 and 2.
-* every scheduling option of the kernel gives the bit-identical image, and so does the pooled-paths experiment
-  (ow.variant = 6, the shared-memory wavefront that was measured and lost: DESIGN.md §4).
+* every scheduling option of the kernel gives the bit-identical image, and so do the two wavefront experiments that
+  were measured and lost (ow.variant = 6: CTA-scope queues in shared memory; ow.variant = 7: the global wavefront,
+  DESIGN.md §4).
 * rays with exactly zero direction components (ADVICE: inf * 0 in the FMA slab test) hit what the oracle hits.
 * oracle-vs-device images at BASELINE.json's sizes, and a t-test for bias per first-hit material.
 """
@@ -136,6 +137,8 @@ OPTION_SETS = [
     {"ow.variant": 6},
     {"ow.variant": 6, "ow.slots": 256, "ow.minb": 3, "ow.exit_min": 4, "ow.svc_lo": 8},
     {"ow.variant": 6, "ow.slots": 512, "ow.exit_min": 16, "ow.leaf_min": 4, "ow.ctas_per_sm": 2},
+    {"ow.variant": 7},                                      # the global wavefront (state in L2 / HBM, two kernels per bounce)
+    {"ow.variant": 7, "ow.slots": 4096, "ow.exit_min": 16},  # far fewer slots than items in flight at once
 ]
 RESET = {"ow.variant": 5, "ow.slots": 0, "ow.minb": 0, "ow.ctas_per_sm": 0, "ow.svc_lo": 0, "ow.exit_min": 0, "ow.leaf_min": 0,
          "ow.svc_min": 0}
