@@ -544,7 +544,7 @@ struct TraceIO {
     const int* self_refs;  // optional: the leaf ref each ray starts on (-1 none)
     rl_hit* hits;
 };
-template <bool COUNT, int MINB, int PRIMS, bool TRACE = false, int OPT = 2>
+template <bool COUNT, int MINB, int PRIMS, bool TRACE = false, int OPT = 3>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
                                                           int sys_queue, int qbatch, int wbatch, long long q_guided, int svc_min,
@@ -768,8 +768,9 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             const int keep = 32 - n_end - leaf_min;
             int n_in;
             do {
-                // OPT node steps per ballot (measured, C4 / C5: 1 -> 12.44 / 67.4 ms, 2 -> 12.11 / 64.7, 3 -> 12.39 / 65.6,
-                // 4 -> 12.63 / 65.4: two halve the ballots while a lane that parks after the first step idles one step only)
+                // OPT node steps per ballot.  Round 1 (58-instruction steps): 1 -> 12.44 / 67.4 ms (C4 / C5 at reduced spp),
+                // 2 -> 12.11 / 64.7, 3 -> 12.39 / 65.6.  Round 2's step is 40 % shorter, so the ballot + loop control weighs
+                // more (13 % of the warp instructions at two steps): 3 -> C4 98.4 -> 97.95 ms, C5 57.7 -> 55.6 ms.
 #pragma unroll
                 for (int k = 0; k < (OPT < 1 ? 1 : OPT); k++) {
                     if (node >= 0) bvh2_step<COUNT, 256>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc, sc.n_bvh_nodes);
