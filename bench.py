@@ -289,7 +289,8 @@ class OwBench:
 
     def parallelism(self):
         if self.world_size == 1:
-            return "1 rank, persistent CTAs, path slots + ready/done rings in shared memory"
+            return ("1 rank, one persistent launch: per-lane paths with resumable traversal, warps take (pixel x sample-chunk) "
+                    "batches from a CTA-level reserve refilled by one global atomic per 512 items")
         how = ("partial sums stored straight into rank 0's HBM over NVLink (fused gather), one 4-byte NCCL all-reduce "
                "per render as the closing rendezvous, alternating queue slots (no pre-launch rendezvous)"
                if self.mgpu == "fused" else "NCCL sum-gather to rank 0")
@@ -549,7 +550,7 @@ def main():
             "clocks": clocks, "gpu_launches": total_launches,
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(B.desc.nbytes()),
                     "d2h_bytes_per_step": int(B.out_bytes), "ms_per_step": e2e_s * 1e3, "steps": e2e_n,
-                    "host_buffer": "pageable (numpy), converted to the f64 Canvas",
+                    "host_buffer": "pageable (numpy); the Canvas holds the f32 frame the device computed and widens it to f64 on first pixel access",
                     "path": "Camera.render(world): lower the object tree -> rl_scene_upload (flatten, H2D, LBVH build) -> render -> D2H",
                     "prepared": {"value": rays / e2e_prep_s / 1e6, "ms_per_step": e2e_prep_s * 1e3,
                                  "path": "Camera.render(scene_desc): the caller keeps the lowered description"}},

@@ -342,14 +342,34 @@ __device__ __forceinline__ float2 ffma2(float2 a, float s, float t) { return ffm
 //  * The push / pop tail has no divergent paths in the common case: selects, one predicated shared-memory store or load
 //    and one predicated pointer add.  Only a lane whose stack is STACK_SM deep takes the generic path.
 //  * A popped node is not culled against the current hit: its children fail their own slab tests.
+// One 32-byte load per lane (sm_100 LDG.E.256): a 64-byte node is 2 load instructions instead of 4.  Every lane of a
+// divergent load touches its own 128-byte line and the L1 spends one wavefront per line PER INSTRUCTION, so halving the
+// instructions halves the LSU wavefronts — the pipe ncu shows at 84 % on the cover scene (profiles/r02_ncu_ow_c4_500.json).
+// p must be 32-byte aligned and the data read-only for the kernel's lifetime (ld.global.nc).
+#ifndef RL_LDG256
+#define RL_LDG256 1
+#endif
+__device__ __forceinline__ void ldg256(const void* p, float4& lo, float4& hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+
 template <bool COUNT, int THREADS>
 __device__ __forceinline__ void bvh2_step(const BvhNode* __restrict__ nodes, int& node, TravStack& st, StackSpill& spill,
                                           const float3 inv_d, const float3 oi, const float tmin, const float tmax,
                                           LocalCount<COUNT>& lc, const int n_nodes = 0x7fffffff) {
     RL_CHECK_OR(node >= 0 && node < n_nodes, lc, { node = TRAV_END; return; });
+#if RL_LDG256
+    float4 a, b, c, dd;
+    ldg256(nodes + node, a, b);
+    ldg256(reinterpret_cast<const char*>(nodes + node) + 32, c, dd);
+    const int2 d = make_int2(__float_as_int(dd.x), __float_as_int(dd.y));
+#else
     const float4* np = reinterpret_cast<const float4*>(nodes + node);
     const float4 a = np[0], b = np[1], c = np[2];
     const int2 d = *reinterpret_cast<const int2*>(np + 3);
+#endif
     if (COUNT) lc.nodes++;
     // both children per instruction: (c0, c1) pairs x scalar 1/d (FFMA2 broadcasts a scalar operand)
     const float2 tcx = ffma2(make_float2(a.x, a.y), inv_d.x, -oi.x);

@@ -19,7 +19,11 @@ cudaError_t launch_rtc_trace(const DevScene& sc, const rl_ray* d_rays, uint64_t 
 // count): `body` chunks of about equal size, then OW_TAIL_CHUNKS chunks of OW_TAIL_SIZE samples.  Items are popped
 // chunk-major, so the LAST items of a render are the small ones: what the slowest warp still holds when every other
 // warp of every GPU has run dry is a 2-sample item, not an 8-sample one (the load-balancing tail of an 8-GPU step).
-constexpr int OW_TAIL_CHUNKS = 8, OW_TAIL_SIZE = 2;
+#ifndef RL_OW_TAIL_CHUNKS  // overridable for tools/build_alt.py experiments only
+#define RL_OW_TAIL_CHUNKS 8
+#define RL_OW_TAIL_SIZE 2
+#endif
+constexpr int OW_TAIL_CHUNKS = RL_OW_TAIL_CHUNKS, OW_TAIL_SIZE = RL_OW_TAIL_SIZE;
 __host__ __device__ inline int ow_tail_chunks(int spp) { return spp >= 64 ? OW_TAIL_CHUNKS : 0; }
 __host__ __device__ inline void ow_chunk_range(int spp, int n_chunks, int chunk, int* s0, int* s1) {
     const int t = ow_tail_chunks(spp), nb = n_chunks - t, body = spp - t * OW_TAIL_SIZE;

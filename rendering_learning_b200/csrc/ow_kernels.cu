@@ -154,7 +154,12 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
         return;
     }
     if (PRIMS == PRIMS_SPHERES || ((PRIMS & PRIMS_SPHERES) && type == REF_SPHERE)) {  // sphere.rs:34-75
+#if RL_LDG256
+        float4 c, dc;
+        ldg256(sc.spheres + idx, c, dc);
+#else
         float4 c = sc.spheres[idx].c, dc = sc.spheres[idx].dc;
+#endif
         if (COUNT) lc.prims++;
         float3 center = fma3(f3(dc), time, f3(c));
         float3 oc = o - center;
@@ -553,6 +558,10 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
     const unsigned lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const uint2 key = make_uint2(cam.seed_lo, cam.seed_hi);
+#ifdef RL_TIMELINE  // experiment build (tools/build_alt.py): warp lifetimes into the statistics counters
+    unsigned long long tl_start, tl_dry = 0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_start));
+#endif
     // item.  Cold per-lane state (touched once per path or once per item, never inside the traversal loop) lives in
     // shared memory, [word][thread] so every access is conflict free; that is ~10 registers the traversal loop gets
     // back (ptxas: the 64-register build spilled 262 B with them in registers).
@@ -654,6 +663,9 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
                 cur_next = start;
                 cur_end = start + take;
                 if (take == 0 && dry) q_dry = true;
+#ifdef RL_TIMELINE
+                if (q_dry && !tl_dry) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_dry));
+#endif
                 if (lane == 0) sm_qfirst[wid] = cur_next;
                 // Decode the WHOLE batch now, with every lane: item -> (job, chunk, pixel, sample range) is ~300 instructions of
                 // 64-bit divisions and a binary search, and round 1 ran it per item at ~2 of 32 lanes — whenever a service
@@ -788,6 +800,17 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             else atomicAdd(queue + 1, (unsigned long long)retired);
         }
     }
+#ifdef RL_TIMELINE
+    if (!COUNT && !TRACE && lane == 0) {
+        unsigned long long tl_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_end));
+        atomicAdd(&counters->rays, 1ull);                                         // warps
+        atomicAdd(&counters->node_visits, tl_end - tl_start);                     // sum of warp lifetimes (ns)
+        atomicAdd(&counters->prim_tests, (tl_dry ? tl_dry : tl_end) - tl_start);  // sum of time until the warp found the queue dry
+        atomicMax(&counters->shades, tl_end - tl_start);                          // longest warp lifetime
+        atomicMax(&counters->tri_tests, tl_dry ? tl_end - tl_dry : 0ull);         // longest drain of one warp
+    }
+#endif
     lc.flush(counters);
 }
 

@@ -39,7 +39,20 @@ struct RtcCam {
 // roots in the reference's push order; returns the count (<= 4)
 // tags: 2 bits per root — 0 wall / body, 1 lower cap, 2 upper cap (f32 cannot re-derive the cap from the
 // hit point with the reference's 1e-8 window, so the root remembers what it is)
-__device__ __forceinline__ int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], unsigned* tags) {
+#ifndef RL_RTC_NOINLINE  // experiment switch (tools/build_alt.py): 1 = prim_roots out of line, 2 = + closest / shadow / n1-n2
+#define RL_RTC_NOINLINE 0
+#endif
+#if RL_RTC_NOINLINE >= 1
+#define RL_ROOTS_FN __device__ __noinline__
+#else
+#define RL_ROOTS_FN __device__ __forceinline__
+#endif
+#if RL_RTC_NOINLINE >= 2
+#define RL_TRACER_FN __device__ __noinline__
+#else
+#define RL_TRACER_FN __device__
+#endif
+RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], unsigned* tags) {
     int n = 0;
     *tags = 0u;
     switch (p.kind) {
@@ -324,7 +337,7 @@ struct RtcTracer {
     }
 
     // closest hit per intersect::hit over World::intersect
-    __device__ RtcHit closest(float3 o, float3 d) {
+    RL_TRACER_FN RtcHit closest(float3 o, float3 d) {
         if (COUNT) lc.rays++;
         RtcHit h;
         h.t = RL_INF;
@@ -382,7 +395,7 @@ struct RtcTracer {
     }
 
     // n1 / n2 of prepare_computations (intersect.rs:72-99) without building the list
-    __device__ void refractive_indices(float3 o, float3 d, const RtcHit& h, float* n1, float* n2) {
+    RL_TRACER_FN void refractive_indices(float3 o, float3 d, const RtcHit& h, float* n1, float* n2) {
         float best_t = -RL_INF;
         int best_node = -1;
         float best_ior = 1.0f;
@@ -467,7 +480,7 @@ struct RtcTracer {
     }
 
     // World::shadow_attenuation (world.rs:104-126)
-    __device__ float shadow(float3 point, float3 light_pos) {
+    RL_TRACER_FN float shadow(float3 point, float3 light_pos) {
         float3 v = light_pos - point;
         float dist2 = dot(v, v);
         if (dist2 == 0.0f) return 1.0f;
@@ -721,9 +734,22 @@ __device__ __forceinline__ void camera_ray(const RtcCam& c, int px, int py, int 
 }
 
 // one thread per pixel; warps walk 8x4 pixel micro-tiles of each job rectangle
+// Resident CTAs per SM the render kernel is compiled for.  Unconstrained, ptxas takes 96 registers (5 CTAs = 20 warps per SM)
+// and ncu shows the kernel waiting on instruction fetch (`no_instruction` 3.5 warps per issue on the mirror scene: 7 000
+// SASS instructions of branchy code) with too few warps to hide it.  Measured at 4K (gpurun_out/abrtc1, abrtc2):
+//   CTAs/SM (registers)   1 (96)    6 (80)    8 (64)    10 (48)   12 (40)
+//   C2 mirror scene       6.40 ms   5.45      4.97      5.33      5.23
+//   C3 teapot             0.676     0.628     0.603     0.618     0.635
+// Out-of-line prim_roots / closest / shadow (smaller code) was slower: 6.65 - 7.28 ms on C2.
+#ifndef RL_RTC_MINB
+#define RL_RTC_MINB 8
+#endif
+#ifndef RL_RTC_MINB_CSG
+#define RL_RTC_MINB_CSG 8
+#endif
 template <bool COUNT, bool CSG>
-__global__ void __launch_bounds__(128) k_rtc_render(DevScene sc, RtcCam cam, JobTable jt, float* __restrict__ out,
-                                                    Counters* counters) {
+__global__ void __launch_bounds__(128, CSG ? RL_RTC_MINB_CSG : RL_RTC_MINB)
+    k_rtc_render(DevScene sc, RtcCam cam, JobTable jt, float* __restrict__ out, Counters* counters) {
     LocalCount<COUNT> lc;
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (item < jt.n_items) {

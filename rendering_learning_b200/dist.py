@@ -254,7 +254,7 @@ def camera_render_ow(camera, world, ctx, buffers):
             return None
         check_fused_complete(ctx, camera.params.abi(), slot, buffers.nc, buffers.H, buffers.W)
     sums = buffers.frame.cpu().numpy()  # pageable
-    return ow.Canvas(camera.params.samples_per_pixel, buffers.W, buffers.H, sums.astype("float64"))
+    return ow.Canvas(camera.params.samples_per_pixel, buffers.W, buffers.H, sums)
 
 
 def camera_render_rtc(camera, world, ctx, buffers):
@@ -270,4 +270,4 @@ def camera_render_rtc(camera, world, ctx, buffers):
         return None
     ctx.synchronize()
     rgb = buffers.frame.cpu().numpy()
-    return rtc.Canvas(camera.hsize, camera.vsize, rgb.astype("float64"))
+    return rtc.Canvas(camera.hsize, camera.vsize, rgb)

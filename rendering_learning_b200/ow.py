@@ -522,7 +522,22 @@ class Canvas:
 
     def __init__(self, samples, width, height, data):
         self.samples, self.width, self.height = int(samples), int(width), int(height)
-        self.data = np.asarray(data, np.float64).reshape(self.height, self.width, 3)
+        if isinstance(data, np.ndarray) and data.dtype == np.float32:
+            # sums straight from the device: held as the f32 they were accumulated in, widened to the reference's f64
+            # `Color` on first access (`data`)
+            self._data = data.reshape(self.height, self.width, 3)
+        else:
+            self._data = np.asarray(data, np.float64).reshape(self.height, self.width, 3)
+
+    @property
+    def data(self) -> np.ndarray:
+        if self._data.dtype != np.float64:
+            self._data = self._data.astype(np.float64)
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = np.asarray(value, np.float64).reshape(self.height, self.width, 3)
 
     def merge(self, other: "Canvas") -> "Canvas":
         assert self.width == other.width
@@ -630,8 +645,7 @@ class Camera:
         sd = world if isinstance(world, SceneDesc) else lower_world(world)
         ctx.scene_upload(sd)
         sums, _ = ctx.render_ow(self.params.abi(), samples_already_rendered)
-        return Canvas(self.params.samples_per_pixel, self.params.image_width, self.image_height,
-                      sums.astype(np.float64))
+        return Canvas(self.params.samples_per_pixel, self.params.image_width, self.image_height, sums)
 
     def render(self, world, ctx=None) -> Canvas:
         """Drop-in for `Camera::render` (camera.rs:122-124)."""

@@ -493,8 +493,24 @@ class Canvas:
 
     def __init__(self, width: int, height: int, data: np.ndarray | None = None):
         self.width, self.height = int(width), int(height)
-        self.data = (np.zeros((self.height, self.width, 3), np.float64) if data is None
-                     else np.asarray(data, np.float64).reshape(self.height, self.width, 3))
+        if data is None:
+            self._data = np.zeros((self.height, self.width, 3), np.float64)
+        elif isinstance(data, np.ndarray) and data.dtype == np.float32:
+            # a frame straight from the device: held as the f32 it was computed in and widened to the reference's f64
+            # `Color` on first pixel access (`data`) — widening a 4K frame costs more than rendering it
+            self._data = data.reshape(self.height, self.width, 3)
+        else:
+            self._data = np.asarray(data, np.float64).reshape(self.height, self.width, 3)
+
+    @property
+    def data(self) -> np.ndarray:
+        if self._data.dtype != np.float64:
+            self._data = self._data.astype(np.float64)
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = np.asarray(value, np.float64).reshape(self.height, self.width, 3)
 
     def at(self, x, y):
         if x >= self.width or y >= self.height:
@@ -599,7 +615,7 @@ class Camera:
         SceneDesc a caller lowered once (`world.lower()`) and keeps across renders."""
         ctx, opts = self._resident(world, opts, ctx)
         rgb, _ = ctx.render_rtc(self.abi(), opts.anti_aliasing_samples)
-        return Canvas(self.hsize, self.vsize, rgb.astype(np.float64))
+        return Canvas(self.hsize, self.vsize, rgb)
 
     def render_ppm(self, world, opts: RenderOpts | None = None, ctx=None) -> str:
         """`camera.render(&world, &opts).ppm()` (draw_scene.rs:42-47) for a caller that only wants the file: the 8-bit

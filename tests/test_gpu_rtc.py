@@ -87,6 +87,17 @@ def test_image_within_one_level(ctx, oracle, name):
     assert abs(img.mean() - ref.mean()) < 2e-4
 
 
+@pytest.mark.parametrize("name,builder", [("C1", lambda: scenes.rtc_three_spheres_scene(1920, 1080)),
+                                          ("C2", lambda: scenes.rtc_mirror_scene(3840, 2160)),
+                                          ("C3", lambda: scenes.rtc_obj_scene(3840, 2160))])
+def test_image_within_one_level_at_baseline_sizes(ctx, oracle, name, builder):
+    """the same bar at BASELINE.json's frame sizes (the f64 oracle renders a 4K frame in a few seconds on the host cores):
+    at 4K a pixel is 1/150 of the 300 x 200 one, so edge pixels are a SMALLER share of the frame, not a larger one"""
+    frac, img, ref = image_parity(ctx, oracle, builder())
+    assert frac <= EDGE_FRACTION, frac
+    assert abs(img.mean() - ref.mean()) < 2e-4
+
+
 def test_anti_aliasing_samples(ctx, oracle):
     frac, img, ref = image_parity(ctx, oracle, scenes.rtc_three_spheres_scene(160, 90), aa=3)
     assert frac <= EDGE_FRACTION

@@ -3,6 +3,10 @@ import hashlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from rendering_learning_b200 import _abi as _A
+_alt = [a for a in sys.argv if a.startswith('lib=')]
+if _alt:  # an experiment build made by tools/build_alt.py
+    sys.argv.remove(_alt[0]); _A.LIB_PATH = os.path.join(os.path.dirname(_A.LIB_PATH), f'librl_b200_{_alt[0][4:]}.so')
 from rendering_learning_b200 import Context, ow, scenes
 wl = sys.argv[1] if len(sys.argv) > 1 else "C4"
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 50
