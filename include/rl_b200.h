@@ -80,6 +80,10 @@ enum {
 
 enum { RL_CSG_UNION = 0, RL_CSG_INTERSECTION = 1, RL_CSG_DIFFERENCE = 2 };
 
+/* A node's id is its index in rl_scene_desc.nodes[].  Ids may be assigned in ANY order: where the reference orders objects
+ * (equal-t ties, "later object wins", RTC/src/scene/intersect.rs:159-168; the n1 / n2 and shadow walks) the library follows
+ * the order a depth-first walk from roots[] meets the leaves — the reference's World / Group order — not the ids; rl_hit.node
+ * reports the caller's id.  A subtree may be referenced from several parents (each reference is its own instance). */
 typedef struct rl_node {
     int32_t kind;
     int32_t material;    /* leaf shapes: index into materials[]; -1 otherwise */

@@ -53,7 +53,7 @@ struct rl_ctx {
     bool instrumented = false;
     bool has_scene = false;
     // scene buffers
-    DevBuf prims, tri_verts, tri_shade, xforms, spheres, quads, sphere_node, quad_node, materials, textures,
+    DevBuf prims, tri_verts, tri_shade, xforms, spheres, quads, sphere_node, quad_node, ord_node, materials, textures,
         images, lights, nodes;
     std::vector<DevBuf> image_texels;
     DevBuf big_refs, csg, media, medium_refs, perlin_vec, perlin_perm, bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
@@ -209,7 +209,7 @@ void rl_destroy(rl_ctx* c) {
     c->shared_partial_own.release();
     c->shared_queue_own.release();
     DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
-                     &c->quad_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
+                     &c->quad_node, &c->ord_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
                      &c->jobs, &c->prefix, &c->frame, &c->frame8, &c->partial, &c->rays, &c->hits, &c->self_refs,
@@ -368,6 +368,7 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
     CK(c, upload(c->quads, fs.quads, s));
     CK(c, upload(c->sphere_node, fs.sphere_node, s));
     CK(c, upload(c->quad_node, fs.quad_node, s));
+    CK(c, upload(c->ord_node, fs.ord_node, s));
     CK(c, upload(c->materials, fs.materials, s));
     CK(c, upload(c->textures, fs.textures, s));
     CK(c, upload(c->lights, fs.lights, s));
@@ -479,6 +480,8 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
     d.quads = c->quads.as<OwQuad>();
     d.sphere_node = c->sphere_node.as<int>();
     d.quad_node = c->quad_node.as<int>();
+    d.ord_node = c->ord_node.as<int>();
+    d.n_ord = (int)fs.ord_node.size();
     d.materials = c->materials.as<DevMaterial>();
     d.textures = c->textures.as<DevTexture>();
     d.images = c->images.as<DevImage>();
@@ -496,7 +499,7 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
     auto note = [&](int node, int ref) { if (node >= 0 && node < (int)c->node_ref.size()) c->node_ref[node] = ref; };
     for (size_t i = 0; i < fs.sphere_node.size(); i++) note(fs.sphere_node[i], make_ref(REF_SPHERE, (int)i));
     for (size_t i = 0; i < fs.quad_node.size(); i++) note(fs.quad_node[i], make_ref(REF_QUAD, (int)i));
-    for (size_t i = 0; i < fs.tri_verts.size(); i++) {
+    for (size_t i = 0; fs.flavor == RL_FLAVOR_OW && i < fs.tri_verts.size(); i++) {  // (RTC triangles carry DFS ordinals there)
         int node;
         memcpy(&node, &fs.tri_verts[i].p1.w, sizeof(int));
         note(node, make_ref(REF_TRI, (int)i));

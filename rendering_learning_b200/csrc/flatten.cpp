@@ -258,6 +258,14 @@ struct Flattener {
 
     // ---- RTC -----------------------------------------------------------------------------------
     // fwd_total: object -> world, inv_total: world -> object
+    // RTC ties at equal t ("later object wins", intersect.rs:159-168; the before() / later() order of n1 / n2 and shadows)
+    // follow the reference's World / Group order = the order this DFS meets the leaves.  Each leaf gets its DFS ordinal,
+    // the device orders by it, and ord_node maps it back to the caller's node id for rl_hit — so the caller's ids may be
+    // in any order, and a subtree referenced twice gets two ordinals.
+    int leaf_ordinal(int id) {
+        fs->ord_node.push_back(id);
+        return (int)fs->ord_node.size() - 1;
+    }
     bool rtc_node(int id, const Aff& fwd_total, const Aff& inv_total, int depth) {
         if (!check_node(id)) return false;
         if (depth > 64) return fail(RL_E_INVALID, "object tree too deep (cycle?)");
@@ -285,7 +293,7 @@ struct Flattener {
                                                                                             : PK_RTC_CONE;
                 p.flags = nd.flags & 1;
                 p.material = nd.material;
-                p.node = id;
+                p.node = leaf_ordinal(id);
                 fs->prims.push_back(p);
                 return true;
             }
@@ -336,11 +344,11 @@ struct Flattener {
                     p.kind = PK_TRIANGLE;
                     p.flags = smooth ? 1 : 0;
                     p.material = nd.material;
-                    p.node = id;
+                    p.node = leaf_ordinal(id);
                     fs->prims.push_back(p);
                     return true;
                 }
-                push_triangle(P, N, nullptr, nd.material, id, (smooth ? 1 : 0) | (xf << 8));
+                push_triangle(P, N, nullptr, nd.material, leaf_ordinal(id), (smooth ? 1 : 0) | (xf << 8));
                 return true;
             }
             case RL_RTC_MESH: {  // io/wavefront_obj.rs:73-76: Bounded<Group<Triangle>> of the ctx's parsed mesh
@@ -351,7 +359,8 @@ struct Flattener {
                 Aff pat;
                 bool has;
                 if (!pattern_xform(nd.material, inv_total, &pat, &has)) return false;
-                FlatScene::MeshUse* u = mesh_use(fwd_total, inv_total, nd.material, id);
+                const int ord = leaf_ordinal(id);  // one ordinal for the mesh: its triangles tie-break by index
+                FlatScene::MeshUse* u = mesh_use(fwd_total, inv_total, nd.material, ord);
                 if (has) {
                     Xform x;
                     store_rows(pat, x.r);
@@ -361,7 +370,7 @@ struct Flattener {
                 u->bvh_first = (int)fs->bvh_ref.size();
                 fs->bvh_aabb.resize(fs->bvh_aabb.size() + 6 * (size_t)mesh->n_triangles, 0.0f);
                 fs->bvh_ref.resize(fs->bvh_ref.size() + (size_t)mesh->n_triangles, 0);
-                fs->bvh_node_id.resize(fs->bvh_node_id.size() + (size_t)mesh->n_triangles, id);
+                fs->bvh_node_id.resize(fs->bvh_node_id.size() + (size_t)mesh->n_triangles, ord);
                 return true;
             }
             case RL_RTC_TRANSFORMED: {
@@ -756,6 +765,7 @@ int flatten_scene(const rl_scene_desc* d, FlatScene* out, std::string* err, cons
         }
         for (int k = 0; k < d->n_roots; k++)
             if (!f.rtc_node(d->roots[k], aff_identity(), aff_identity(), 0)) return f.rc;
+        for (int& v : out->bvh_node_id) v = out->ord_node[v];  // rl_scene_info reports the caller's node ids
     } else {
         if (d->n_roots != 1) {
             *err = "an OW scene has exactly one root hittable";

@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(128) k_rtc_trace(DevScene sc, const rl_ray* __
         RtcTracer<COUNT, CSG> tr(sc, lc);
         RtcHit h = tr.closest(f3(r.origin[0], r.origin[1], r.origin[2]), f3(r.direction[0], r.direction[1], r.direction[2]));
         rl_hit o;
-        o.node = h.prim == NO_HIT ? -1 : h.node;
+        o.node = (h.prim == NO_HIT || h.node < 0 || h.node >= sc.n_ord) ? -1 : sc.ord_node[h.node];  // DFS ordinal -> caller's id
         o.t = h.t;
         o.u = h.b1;
         o.v = h.b2;

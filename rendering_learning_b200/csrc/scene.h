@@ -138,6 +138,8 @@ struct DevScene {
     const float4* perlin_vec;  // [n_perlins][256] gradient vectors
     const int* perlin_perm;    // [n_perlins][3][256] perm_x, perm_y, perm_z
     const int4* csg;  // (operation, lo, mid, hi): left child = prims [lo, mid), right child = prims [mid, hi)
+    const int* ord_node;  // RTC: DFS leaf ordinal (RtcPrim.node, TriVerts.p1.w) -> the caller's node id
+    int n_ord;
 };
 
 // host-side result of flattening
@@ -159,6 +161,7 @@ struct FlatScene {
     std::vector<float> bvh_aabb;   // [n][6]
     std::vector<int> bvh_ref;      // [n]
     std::vector<int> bvh_node_id;  // [n]
+    std::vector<int> ord_node;     // RTC: DFS leaf ordinal -> the caller's node id (flatten.cpp leaf_ordinal)
     std::vector<int> big_refs;     // OW leaf refs kept out of the LBVH (OW_BIG_RADIUS)
     std::vector<int4> csg;         // RTC CSG nodes, post-order
     std::vector<OwMedium> media;

@@ -357,3 +357,58 @@ def test_device_side_u8_encoder_matches_canvas_ppm(ctx):
     img, _ = ctx.render_rtc(sc.camera.abi(), 1)
     u8dev, _ = ctx.render_rtc_u8(sc.camera.abi(), 1)
     assert img.max() > 1.0 and np.array_equal(u8dev.astype(np.int64), u8(img.astype(np.float64)))
+
+
+def renumbered(desc, perm):
+    """the same object tree with node i stored at index perm[i] (node ids are the caller's to choose: the ABI fixes no order)"""
+    import copy
+    out = copy.copy(desc)
+    out._frozen = None
+    direct = {A.RL_RTC_TRANSFORMED: (True, False), A.RL_RTC_BOUNDED: (True, False), A.RL_RTC_CSG: (True, True)}
+    nodes = [None] * len(desc.nodes)
+    for i, (kind, mat, cb, ce, flags, param) in enumerate(desc.nodes):
+        b, e = direct.get(kind, (False, False))
+        nodes[perm[i]] = (kind, mat, perm[cb] if b else cb, perm[ce] if e else ce, flags, param)
+    out.nodes = nodes
+    out.children = [perm[c] for c in desc.children]
+    out.roots = [perm[r] for r in desc.roots]
+    return out
+
+
+def test_ties_follow_the_tree_order_not_the_node_ids(ctx, oracle):
+    """intersect.rs:159-168: among hits at the same t the LATER object of the World wins (and the n1 / n2 and shadow walks
+    order coincident crossings the same way).  Coincident surfaces — two spheres of different colour in one place, glass
+    inside glass of the same radius, a cube face on the floor plane — rendered from the lowered tree and from the same tree
+    with its node ids reversed / shuffled: identical frames, and the hit reports carry the caller's ids."""
+    glass = lambda ri: rtc.Material(surface=(0.1, 0.1, 0.1), transparency=0.9, reflectivity=0.3, refractive_index=ri,
+                                    diffuse=0.1, ambient=0.0)
+    at = lambda obj, *m: rtc.Transformed.new(obj, T.sequence(list(m)))
+    objs = [
+        rtc.Plane(rtc.Material(surface=rtc.Checker3d(a=(0.9, 0.9, 0.9), b=(0.2, 0.2, 0.2)), reflectivity=0.1)),
+        at(rtc.Sphere(rtc.Material(surface=(1.0, 0.1, 0.1))), T.translation(-2.5, 1.0, 0.0)),
+        at(rtc.Sphere(rtc.Material(surface=(0.1, 0.1, 1.0))), T.translation(-2.5, 1.0, 0.0)),
+        at(rtc.Sphere(glass(1.5)), T.translation(0.0, 1.0, 0.0)),
+        at(rtc.Sphere(glass(2.0)), T.translation(0.0, 1.0, 0.0)),
+        at(rtc.Cube(rtc.Material(surface=(0.1, 0.8, 0.1))), T.translation(2.5, 1.0, 0.0)),
+        at(rtc.Cube(rtc.Material(surface=(0.8, 0.8, 0.1))), T.scaling(1.0, 1.0, 0.5), T.translation(2.5, 1.0, 0.0)),
+    ]
+    world = rtc.World(objects=objs, lights=[rtc.PointLight((-6.0, 8.0, -8.0), (1.0, 1.0, 1.0))])
+    cam = rtc.Camera.new(320, 200, math.pi / 3, T.view_transform((0.0, 2.5, -8.0), (0.0, 1.0, 0.0), (0.0, 1.0, 0.0)))
+    desc = world.lower()
+    ctx.scene_upload(desc)
+    base, _ = ctx.render_rtc(cam.abi(), 1)
+    ref = oracle.rtc_render(desc, cam.abi(), 1)
+    assert (np.abs(u8(base.astype(np.float64)) - u8(ref)) > 1).any(axis=2).mean() <= EDGE_FRACTION
+    rays = oracle.rtc_camera_rays(cam.abi(), 1).astype(np.float32)
+    hits0 = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6])
+    n = len(desc.nodes)
+    rng = np.random.default_rng(5)
+    for perm in (list(range(n - 1, -1, -1)), list(rng.permutation(n))):
+        d2 = renumbered(desc, [int(p) for p in perm])
+        ctx.scene_upload(d2)
+        img, _ = ctx.render_rtc(cam.abi(), 1)
+        assert np.array_equal(img, base)
+        hits = ctx.trace_batch(rays[:, 0:3], rays[:, 3:6])
+        inv = np.full(n + 1, -1)
+        inv[np.asarray(perm)] = np.arange(n)
+        assert np.array_equal(inv[hits["node"]], hits0["node"]) and np.array_equal(hits["t"], hits0["t"])
