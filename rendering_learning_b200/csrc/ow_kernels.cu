@@ -495,6 +495,9 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
 // NVLink when the counter is rank 0's — overlaps rendering.  Round 1 (and the first half of round 2) popped the global
 // counter once per WARP batch: 790 k same-address atomics per cover-scene step, 56 M/s at 8 GPUs, all landing on one L2
 // slice of GPU 0 — the ~1.7 ms per step that did not scale (14.0 ms at 8 GPUs against 12.3 ms = 98.5 / 8).
+#ifndef RL_GUIDED_WCAP
+#define RL_GUIDED_WCAP 64
+#endif
 struct ItemReserve {
     volatile int it_lock, it_dry, nx_size;
     volatile long long it_next, it_end;
@@ -533,6 +536,9 @@ __device__ __forceinline__ int items_take(ItemReserve& ctl, int n, long long n_i
         ctl.it_end = en;
     }
     const long long avail = en - nx;
+    // in the guided phase (small refills near the end of the queue) a warp takes at most RL_GUIDED_WCAP items at a time, so
+    // that what a lane still owns when the queue runs dry is one item, not two or three
+    if (n > RL_GUIDED_WCAP && n_items - nx <= q_guided) n = RL_GUIDED_WCAP;
     const int take = (long long)n < avail ? n : (int)avail;
     *start = nx;
     ctl.it_next = nx + take;
@@ -549,7 +555,10 @@ struct TraceIO {
     const int* self_refs;  // optional: the leaf ref each ray starts on (-1 none)
     rl_hit* hits;
 };
-template <bool COUNT, int MINB, int PRIMS, bool TRACE = false, int OPT = 3>
+#ifndef RL_OW_OPT  // node steps per ballot; experiment builds override it (tools/build_alt.py)
+#define RL_OW_OPT 3
+#endif
+template <bool COUNT, int MINB, int PRIMS, bool TRACE = false, int OPT = RL_OW_OPT>
 __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam, JobTable jt, float* __restrict__ partial,
                                                           unsigned long long* __restrict__ queue, Counters* counters,
                                                           int sys_queue, int qbatch, int wbatch, long long q_guided, int svc_min,
@@ -782,7 +791,9 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             do {
                 // OPT node steps per ballot.  Round 1 (58-instruction steps): 1 -> 12.44 / 67.4 ms (C4 / C5 at reduced spp),
                 // 2 -> 12.11 / 64.7, 3 -> 12.39 / 65.6.  Round 2's step is 40 % shorter, so the ballot + loop control weighs
-                // more (13 % of the warp instructions at two steps): 3 -> C4 98.4 -> 97.95 ms, C5 57.7 -> 55.6 ms.
+                // more (13 % of the warp instructions at two steps): 3 -> C4 98.4 -> 97.95 ms, C5 57.7 -> 55.6 ms; 4 -> 98.1 / 56.0
+                // against 96.5 / 55.7 at 3.  Running the step for ALL lanes under predicates instead of branching around it
+                // (no BSSY / BRA / BSYNC per step) was 8 % slower: 104.4 - 108.4 ms (gpurun_out/ab2).
 #pragma unroll
                 for (int k = 0; k < (OPT < 1 ? 1 : OPT); k++) {
                     if (node >= 0) bvh2_step<COUNT, 256>(sc.nodes, node, st, spill, inv_d, oi, tmin, hit.t, lc, sc.n_bvh_nodes);
@@ -1543,9 +1554,13 @@ __global__ void k_encode_ow_u8(const float* __restrict__ sum, uint8_t* __restric
 // chunk is the unit of work a path slot owns, so it bounds both the load-balancing tail (a 32-sample item was 1.7 ms of
 // lane time, 10 % of an 8-GPU cover-scene step) and the size of the partial-sum buffer (<= 64 frames).  A function of
 // spp ALONE: every rank of a multi-GPU render computes the same partition (round 1 read two environment variables here).
+#ifndef RL_OW_MIN_CHUNK  // overridable for tools/build_alt.py experiments only
+#define RL_OW_MIN_CHUNK 8
+#define RL_OW_MAX_CHUNKS 64
+#endif
 int ow_num_chunks(int spp) {
     if (spp <= 0) return 1;
-    constexpr int min_chunk = 8, max_chunks = 64;
+    constexpr int min_chunk = RL_OW_MIN_CHUNK, max_chunks = RL_OW_MAX_CHUNKS;
     const int t = ow_tail_chunks(spp), body = spp - t * OW_TAIL_SIZE;
     int per_chunk = (body + (max_chunks - t) - 1) / (max_chunks - t);
     if (per_chunk < min_chunk) per_chunk = min_chunk;

@@ -13,7 +13,8 @@ world = scenes.ow_cover_world()
 ctx.scene_upload(ow.lower_world(world))
 import torch
 rows = []
-for spp in (8, 16, 32, 63, 64, 125, 250, 500):
+quick = 'quick' in sys.argv
+for spp in (() if quick else (8, 16, 32, 63, 64, 125, 250, 500)):
     params = scenes.ow_cover_params(samples_per_pixel=spp)
     cam = params.abi()
     W, H, nc = cam.image_width, ctx.ow_image_height(cam), ctx.ow_num_chunks(cam)
@@ -21,9 +22,10 @@ for spp in (8, 16, 32, 63, 64, 125, 250, 500):
     ts = [ctx.render_ow_device(cam, 0, [(0, 0, W, H, 0, nc)], partial.data_ptr()).kernel_ms for _ in range(4)]
     rows.append((spp, min(ts[1:]), nc))
     print(f"spp {spp:4d}  chunks {nc:3d}  kernel {min(ts[1:]):8.3f} ms", flush=True)
-x = np.array([r[0] for r in rows], float); y = np.array([r[1] for r in rows])
-a, b = np.polyfit(x[3:], y[3:], 1)
-print(f"fit over spp >= 63: {a:.4f} ms/spp + {b:.3f} ms")
+if rows:
+    x = np.array([r[0] for r in rows], float); y = np.array([r[1] for r in rows])
+    a, b = np.polyfit(x[3:], y[3:], 1)
+    print(f"fit over spp >= 63: {a:.4f} ms/spp + {b:.3f} ms")
 
 # one eighth of the frame (rows 3H/8 .. 4H/8): the share one GPU of eight gets; intercept of kernel time against spp
 pts = []
@@ -38,7 +40,7 @@ for spp in (125, 250, 375, 500):
     print(f"strip rows {y0}..{y0 + H // 8}: spp {spp:4d} chunks {nc:3d} kernel {t:8.3f} ms", flush=True)
 a, b = np.polyfit([p[0] for p in pts], [p[1] for p in pts], 1)
 print(f"strip fit: {a:.5f} ms/spp + {b:.3f} ms  (500 spp: {pts[-1][1]:.3f} ms, of which {b / pts[-1][1] * 100:.1f} % fixed)")
-if _alt and _alt[0].startswith("lib=timeline"):  # the RL_TIMELINE experiment build reports warp lifetimes in the counters
+if _alt and _alt[0].startswith(("lib=timeline", "lib=tl")):  # the RL_TIMELINE experiment build reports warp lifetimes in the counters
     for spp, rows in ((500, None), (500, 8), (125, 8)):
         params = scenes.ow_cover_params(samples_per_pixel=spp)
         cam = params.abi()
