@@ -16,6 +16,8 @@ for k, v in opts.items():
     ctx.set_option(k, int(v))
 if wl == "C4":
     world, params = scenes.ow_cover_world(), scenes.ow_cover_params(samples_per_pixel=spp)
+elif wl == "C5full":  # the bench configuration: 3840 x 2160
+    world, params = scenes.ow_cow_world(), scenes.ow_cow_params(image_width=3840, samples_per_pixel=spp)
 elif wl == "C5":
     world, params = scenes.ow_cow_world(), scenes.ow_cow_params(image_width=1920, samples_per_pixel=spp)
 else:
