@@ -308,8 +308,9 @@ int rl_trace_batch(rl_ctx* ctx, const rl_ray* rays, uint64_t n, rl_hit* out);
 /* OW only.  The same, for rays that START on a surface (the scattered rays of camera.rs:248-255): self_nodes[i] is the
  * leaf node ray i starts on, or -1.  The reference relies on f64 and t_min = 1e-10 (camera.rs:242) not to re-hit that
  * surface at t ~ 0; the f32 device path instead never re-hits the planar primitive a ray starts on and takes only the FAR
- * root of its own sphere.  OW rays, with or without self nodes, run through the render kernel's own traversal (ready /
- * done queues, big list at ray start, node steps, leaf rounds): this is the production code path, not a second one.
+ * root of its own sphere.  OW rays, with or without self nodes, run through the render kernel itself (a TRACE instantiation
+ * of k_ow_render5: work items are ray indices, the same big list at ray start, node steps, leaf rounds and service
+ * thresholds): this is the production code path, not a second one.
  * t_min is the renderer's: 1e-5 * max|origin_k| + 1e-6 in units of the NORMALISED direction. */
 int rl_trace_batch_ex(rl_ctx* ctx, const rl_ray* rays, const int32_t* self_nodes, uint64_t n, rl_hit* out);
 
