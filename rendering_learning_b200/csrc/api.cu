@@ -53,7 +53,7 @@ struct rl_ctx {
     bool instrumented = false;
     bool has_scene = false;
     // scene buffers
-    DevBuf prims, tri_verts, tri_shade, xforms, spheres, quads, sphere_node, quad_node, ord_node, materials, textures,
+    DevBuf prims, tri_verts, tri_shade, tri_plane, xforms, spheres, quads, sphere_node, quad_node, ord_node, materials, textures,
         images, lights, nodes;
     std::vector<DevBuf> image_texels;
     DevBuf big_refs, csg, media, medium_refs, perlin_vec, perlin_perm, bvh_aabb, bvh_ref, bvh_node_id, bounds, keys, sorted_prim, keys_tmp, idx_tmp, left, right, parent,
@@ -208,7 +208,7 @@ void rl_destroy(rl_ctx* c) {
     if (c->shared_partial_imported && c->shared_partial) cudaIpcCloseMemHandle(c->shared_partial);
     c->shared_partial_own.release();
     c->shared_queue_own.release();
-    DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
+    DevBuf* all[] = {&c->prims, &c->tri_verts, &c->tri_shade, &c->tri_plane, &c->xforms, &c->spheres, &c->quads, &c->sphere_node,
                      &c->quad_node, &c->ord_node, &c->materials, &c->textures, &c->images, &c->lights, &c->nodes, &c->big_refs, &c->csg, &c->media, &c->medium_refs, &c->perlin_vec, &c->perlin_perm, &c->bvh_aabb,
                      &c->bvh_ref, &c->bvh_node_id, &c->bounds, &c->keys, &c->sorted_prim, &c->keys_tmp, &c->idx_tmp,
                      &c->left, &c->right, &c->parent, &c->node_aabb, &c->lbvh_counters, &c->counters, &c->queue,
@@ -419,6 +419,11 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
                                    c->bvh_ref.as<int>(), c->bvh_node_id.as<int>(), s));
         c->upload_launches++;
     }
+    if (fs.flavor == RL_FLAVOR_OW && !fs.tri_verts.empty()) {  // the plane form of every triangle, host-flattened or instanced above
+        CK(c, c->tri_plane.reserve(fs.tri_verts.size() * sizeof(OwTriPlane)));
+        CK(c, launch_tri_planes(c->tri_verts.as<TriVerts>(), (int)fs.tri_verts.size(), c->tri_plane.as<OwTriPlane>(), s));
+        c->upload_launches++;
+    }
     if (n > 0) {
         CK(c, c->bounds.reserve(6 * sizeof(float)));
         CK(c, c->keys.reserve(n * sizeof(uint64_t)));
@@ -475,6 +480,7 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
     d.prims = c->prims.as<RtcPrim>();
     d.tri_verts = c->tri_verts.as<TriVerts>();
     d.tri_shade = c->tri_shade.as<TriShade>();
+    d.tri_plane = c->tri_plane.as<OwTriPlane>();
     d.xforms = c->xforms.as<Xform>();
     d.spheres = c->spheres.as<OwSphere>();
     d.quads = c->quads.as<OwQuad>();

@@ -49,6 +49,7 @@ struct OwTuning {
     int leaf_min = 0;     // parked lanes per leaf round
     int svc_min = 0;      // v5: lanes that must wait before the warp services them
 };
+cudaError_t launch_tri_planes(const TriVerts* d_verts, int n, OwTriPlane* d_planes, cudaStream_t stream);
 int ow_num_chunks(int spp);
 int ow_image_height(const rl_ow_camera* c);
 cudaError_t launch_ow_render(const DevScene& sc, const rl_ow_camera* cam, uint32_t first_sample, const JobTable& jt,

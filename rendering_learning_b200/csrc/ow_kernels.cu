@@ -142,6 +142,7 @@ template <bool COUNT, int PRIMS>
 __device__ __forceinline__ void ow_medium_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
                                                float tmin, unsigned ray_rnd, OwHit& h, LocalCount<COUNT>& lc);
 
+constexpr float OW_TRI_EDGE_EPS = 2e-5f;
 template <bool COUNT, int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const RayPre& pre, float a_dd, float time,
                                              int self_ref, float tmin, OwHit& h, LocalCount<COUNT>& lc, unsigned ray_rnd = 0u) {
@@ -208,18 +209,29 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             return;
         }
         return;
-    } else if ((PRIMS & PRIMS_TRIS) && type == REF_TRI) {  // flat/triangle.rs:60-95 (watertight test instead of the plane basis)
+    } else if ((PRIMS & PRIMS_TRIS) && type == REF_TRI) {  // flat/plane.rs:51-80 + flat/triangle.rs:60-67, the reference's own form
+        // Round 1 ran the watertight ray-space test here (device.cuh tri_hit, still the RTC path): ~90 instructions with its
+        // per-ray axis permutation selects, 20 % of the Cornell-box + spot warp instructions at 5 - 6 lanes
+        // (profiles/r02_lines_ow_c5_4k_256.txt).  The plane form is the quad test with a different acceptance: ~35.
         if (ref == self_ref) return;
-        float4 p0 = sc.tri_verts[idx].p0, p1 = sc.tri_verts[idx].p1, p2 = sc.tri_verts[idx].p2;
+        const OwTriPlane& tp = sc.tri_plane[idx];
+        float4 n4 = tp.n;
         if (COUNT) lc.tris++;
-        float t, b1, b2;
-        if (tri_hit(pre, f3(p0), f3(p1), f3(p2), &t, &b1, &b2) && t >= tmin && t < h.t) {
-            h.t = t;
-            h.ref = ref;
-            h.b1 = b1;
-            h.b2 = b2;
-            return;
-        }
+        float denom = dot(f3(n4), d);
+        if (fabsf(denom) < 1e-8f) return;
+        float t = (n4.w - dot(f3(n4), o)) / denom;
+        if (!(t >= tmin && t < h.t)) return;
+        float3 ip = fma3(d, t, o);
+        float4 a4 = tp.a, b4 = tp.b;
+        float alpha = dot(f3(a4), ip) - a4.w;
+        float beta = dot(f3(b4), ip) - b4.w;
+        // f32 evaluates alpha / beta to ~1e-5 for a unit-sized triangle a few hundred units from the origin; the acceptance is
+        // widened by that much so that the triangles of a mesh overlap along shared edges instead of leaving cracks
+        if (!(alpha >= -OW_TRI_EDGE_EPS && beta >= -OW_TRI_EDGE_EPS && alpha + beta <= 1.0f + OW_TRI_EDGE_EPS)) return;
+        h.t = t;
+        h.ref = ref;
+        h.b1 = alpha;
+        h.b2 = beta;
         return;
     } else if ((PRIMS & PRIMS_QUADS) && type == REF_QUAD) {  // quad: flat/plane.rs:51-80 + flat/quad.rs:37-42
         if (ref == self_ref) return;
@@ -301,10 +313,7 @@ __device__ __forceinline__ void ow_leaf_test_od(const DevScene& sc, int ref, flo
     RayPre pre;
     pre.o = o;
     pre.d = d;
-    if (PRIMS & PRIMS_TRIS) {
-        pre.kx = sh.k & 3; pre.ky = (sh.k >> 2) & 3; pre.kz = (sh.k >> 4) & 3;
-        pre.Sx = sh.Sx; pre.Sy = sh.Sy; pre.Sz = sh.Sz;
-    }
+    (void)sh;  // the OW triangle test is the plane form since round 2: no per-ray shear constants
     // the v5 kernel normalises every ray direction when its traversal starts, so a = d.d is the CONSTANT 1 here and
     // the divisions by it in the sphere test fold away (they were ~16 instructions per test)
     ow_leaf_test<COUNT, PRIMS>(sc, ref, pre, 1.0f, time, self_ref, tmin, h, lc, ray_rnd);
@@ -763,7 +772,6 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             inv_d = safe_inv_fast(p.d);
             oi = p.o * inv_d;
             tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // ow_tmin with |d| = 1
-            if (PRIMS & PRIMS_TRIS) shear = make_shear(p.o, p.d);
             if ((PRIMS & PRIMS_MEDIA) && !TRACE)
                 ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
@@ -1554,6 +1562,47 @@ __global__ void k_encode_ow_u8(const float* __restrict__ sum, uint8_t* __restric
 // chunk is the unit of work a path slot owns, so it bounds both the load-balancing tail (a 32-sample item was 1.7 ms of
 // lane time, 10 % of an 8-GPU cover-scene step) and the size of the partial-sum buffer (<= 64 frames).  A function of
 // spp ALONE: every rank of a multi-GPU render computes the same partition (round 1 read two environment variables here).
+namespace {
+// OwTriPlane from the f32 vertices the scene holds (flat/plane.rs:23-40: n = u x v, normal = n / |n|, d = normal . q,
+// w = n / (n . n); alpha = w . ((p - q) x v) = (v x w) . p - (v x w) . q and beta = w . (u x (p - q)) = (w x u) . p - (w x u) . q by
+// the cyclic symmetry of the triple product).  f64, roundings pinned, one thread per triangle.  A degenerate triangle
+// (u parallel to v: `Plane::new` panics in the reference) gets NaN vectors and is never hit.
+__global__ void k_tri_planes(const TriVerts* __restrict__ tv, int n, OwTriPlane* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p0 = tv[i].p0, p1 = tv[i].p1, p2 = tv[i].p2;
+    const double Q[3] = {p0.x, p0.y, p0.z};
+    const double U[3] = {__dsub_rn(p1.x, p0.x), __dsub_rn(p1.y, p0.y), __dsub_rn(p1.z, p0.z)};
+    const double V[3] = {__dsub_rn(p2.x, p0.x), __dsub_rn(p2.y, p0.y), __dsub_rn(p2.z, p0.z)};
+    auto cross = [](const double* a, const double* b, double* c) {
+        c[0] = __dsub_rn(__dmul_rn(a[1], b[2]), __dmul_rn(a[2], b[1]));
+        c[1] = __dsub_rn(__dmul_rn(a[2], b[0]), __dmul_rn(a[0], b[2]));
+        c[2] = __dsub_rn(__dmul_rn(a[0], b[1]), __dmul_rn(a[1], b[0]));
+    };
+    auto dot3 = [](const double* a, const double* b) {
+        return __dadd_rn(__dadd_rn(__dmul_rn(a[0], b[0]), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+    };
+    double N[3], W[3], A[3], B[3], un[3];
+    cross(U, V, N);
+    const double nn = dot3(N, N), len = __dsqrt_rn(nn);
+    for (int k = 0; k < 3; k++) { un[k] = __ddiv_rn(N[k], len); W[k] = __ddiv_rn(N[k], nn); }
+    cross(V, W, A);
+    cross(W, U, B);
+    OwTriPlane o;
+    o.n = make_float4((float)un[0], (float)un[1], (float)un[2], (float)dot3(un, Q));
+    o.a = make_float4((float)A[0], (float)A[1], (float)A[2], (float)dot3(A, Q));
+    o.b = make_float4((float)B[0], (float)B[1], (float)B[2], (float)dot3(B, Q));
+    out[i] = o;
+}
+
+}  // namespace
+
+cudaError_t launch_tri_planes(const TriVerts* d_verts, int n, OwTriPlane* d_planes, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    k_tri_planes<<<(n + 127) / 128, 128, 0, stream>>>(d_verts, n, d_planes);
+    return cudaGetLastError();
+}
+
 #ifndef RL_OW_MIN_CHUNK  // overridable for tools/build_alt.py experiments only
 #define RL_OW_MIN_CHUNK 8
 #define RL_OW_MAX_CHUNKS 64

@@ -49,6 +49,15 @@ struct TriVerts {
     float4 p1;  // xyz, w = source node id (int bits)
     float4 p2;  // xyz, w = flags (bit0 smooth normals, bit1 has uv) | (xform index + 1) << 8
 };
+// OW triangle in the reference's own form (flat/plane.rs:23-80 + flat/triangle.rs:60-67): plane (unit normal, d) and the two
+// vectors that turn a point of the plane into (alpha, beta) with one dot product each — the layout of OwQuad's first 48 bytes.
+// Derived ON THE DEVICE from the f32 TriVerts (ow_kernels.cu k_tri_planes, f64 arithmetic), so host-flattened and
+// device-ingested triangles share one code path and the same bits.
+struct OwTriPlane {
+    float4 n;  // unit normal, w = d = n . p0
+    float4 a;  // alpha = a.xyz . p - a.w   (weight of p1)
+    float4 b;  // beta  = b.xyz . p - b.w   (weight of p2)
+};
 struct TriShade {
     float4 s0;  // n0.xyz, uv0.x      (flat: n0 = the face normal, world space)
     float4 s1;  // n1.xyz, uv0.y
@@ -122,6 +131,7 @@ struct DevScene {
     const RtcPrim* prims;
     const TriVerts* tri_verts;
     const TriShade* tri_shade;
+    const OwTriPlane* tri_plane;  // OW only, [n_tris]
     const Xform* xforms;
     const OwSphere* spheres;
     const OwQuad* quads;
