@@ -43,11 +43,22 @@ __device__ __forceinline__ uint4 philox(uint4 c, uint2 k) {
 __device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
 // uniform point on the unit sphere (any unbiased sampler gives statistical parity with UnitSphere)
+// MUFU-based square root and sine / cosine for SAMPLING (random directions, lens points) and for the sphere test's root:
+// 1-2 ulp instead of correctly rounded, ~2 instructions instead of ~10 / ~25 (sincospif was 2.6 % of the cover scene's
+// warp instructions at 10-16 lanes).  The angle is kept in [-pi, pi), where sin.approx / cos.approx are accurate to 2^-21.
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void fast_sincos_turn(float u, float* s, float* c) {  // angle = 2 pi u - pi, u in [0, 1)
+    __sincosf(fmaf(u, 6.28318530717959f, -3.14159265358979f), s, c);
+}
 __device__ __forceinline__ float3 unit_vector(float u1, float u2) {
     float z = 1.0f - 2.0f * u1;
-    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float r = fast_sqrt(fmaxf(0.0f, 1.0f - z * z));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    fast_sincos_turn(u2, &s, &c);
     return f3(r * c, r * s, z);
 }
 
@@ -196,7 +207,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             float3 perp = fma3(d, tc, oc);
             float disc = a_dd * (c.w * c.w - dot(perp, perp));
             if (disc < 0.0f) return;
-            float q = sqrtf(disc) / a_dd;
+            float q = fast_sqrt(disc) / a_dd;
             t = tc - q;
             if (!(t >= tmin && t <= h.t)) {
                 t = tc + q;
@@ -219,7 +230,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
         if (COUNT) lc.tris++;
         float denom = dot(f3(n4), d);
         if (fabsf(denom) < 1e-8f) return;
-        float t = (n4.w - dot(f3(n4), o)) / denom;
+        float t = __fdividef(n4.w - dot(f3(n4), o), denom);  // 2 ulp (|denom| >= 1e-8): far below the cancellation in the numerator
         if (!(t >= tmin && t < h.t)) return;
         float3 ip = fma3(d, t, o);
         float4 a4 = tp.a, b4 = tp.b;
@@ -240,7 +251,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
         if (COUNT) lc.prims++;
         float denom = dot(f3(n4), d);
         if (fabsf(denom) < 1e-8f) return;
-        float t = (n4.w - dot(f3(n4), o)) / denom;
+        float t = __fdividef(n4.w - dot(f3(n4), o), denom);  // 2 ulp (|denom| >= 1e-8): far below the cancellation in the numerator
         if (!(t >= tmin && t < h.t)) return;
         float3 ip = fma3(d, t, o);
         float4 a4 = qd.a, b4 = qd.b;
@@ -468,9 +479,9 @@ __device__ __forceinline__ void ow_camera_ray(const OwCam& cam, int i, int j, un
     float3 origin = cam.lookfrom;
     if (cam.defocus) {
         // uniform point in the unit disc (polar map; UnitDisc's rejection loop is statistically identical)
-        float rr = sqrtf(u01(r.w));
+        float rr = fast_sqrt(u01(r.w));
         float s, c;
-        sincospif(2.0f * u01(r.y), &s, &c);
+        fast_sincos_turn(u01(r.y), &s, &c);
         origin = cam.lookfrom + cam.disk_u * (rr * c) + cam.disk_v * (rr * s);
     }
     p.o = origin;

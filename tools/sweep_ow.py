@@ -62,6 +62,11 @@ else:
           for v in itertools.product((3, 4), (256, 320, 384, 512), (6, 8, 12), (8, 16, 24), (6, 8, 12))]
 
 t0 = time.time()
+if mode == "c5":  # thresholds of the triangle-scene instantiation only
+    grid = [{}] + [{"ow.svc_min": a, "ow.leaf_min": b} for a in (12, 16, 20, 24, 28) for b in (4, 8, 12, 16)] + [{"ow.minb": 3}]
+    run("C5_1920x1080_64spp", scenes.ow_cow_world(), scenes.ow_cow_params(image_width=1920, samples_per_pixel=64), grid, reps=3)
+    print(json.dumps({"seconds": time.time() - t0}), flush=True)
+    sys.exit(0)
 w, p = scenes.ow_test_scene()
 p.samples_per_pixel = 32
 run("test_scene_300x168_32spp", w, p, v5 + g6[:6], reps=2)
