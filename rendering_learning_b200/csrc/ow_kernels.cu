@@ -111,10 +111,12 @@ __device__ __forceinline__ float3 tex_value(const DevScene& sc, int tex, float u
     DevTexture t = sc.textures[tex];
     for (int guard = 0; guard < 8 && __float_as_int(t.a.w) == RL_TEX_OW_CHECKER; guard++) {
         float inv_scale = t.b.w;  // texture.rs:42-54
-        long long xi = (long long)floorf(p.x * inv_scale);
-        long long yi = (long long)floorf(p.y * inv_scale);
-        long long zi = (long long)floorf(p.z * inv_scale);
-        bool even = ((xi + yi + zi) % 2) == 0;
+        // `floor() as i64`, summed, `% 2 == 0`: only the parity matters, and the parity of a wrapping 32-bit sum is the sum's
+        // (one F2I with round-down per axis instead of the 64-bit conversions; exact below 2^31 cells from the origin)
+        int xi = __float2int_rd(p.x * inv_scale);
+        int yi = __float2int_rd(p.y * inv_scale);
+        int zi = __float2int_rd(p.z * inv_scale);
+        bool even = (((unsigned)xi + (unsigned)yi + (unsigned)zi) & 1u) == 0u;
         t = sc.textures[even ? t.idx.x : t.idx.y];
     }
     if (__float_as_int(t.a.w) == RL_TEX_OW_IMAGE) {  // texture.rs:63-81

@@ -39,6 +39,19 @@ struct RtcCam {
 // roots in the reference's push order; returns the count (<= 4)
 // tags: 2 bits per root — 0 wall / body, 1 lower cap, 2 upper cap (f32 cannot re-derive the cap from the
 // hit point with the reference's 1e-8 window, so the root remembers what it is)
+// Root divisions: x * rcp.approx(y), 2 ulp, same inf / NaN behaviour as IEEE for y = 0 (the cube's axis-parallel rays).  The
+// IEEE sequence was ~15 % of the mirror scene's warp instructions (profiles/r02_lines_rtc_c2.txt: plane, cube and sphere roots);
+// RL_RTC_IEEE_DIV=1 restores it (tools/build_alt.py A/B).
+#ifndef RL_RTC_IEEE_DIV
+#define RL_RTC_IEEE_DIV 0
+#endif
+__device__ __forceinline__ float fdiv(float x, float y) {
+#if RL_RTC_IEEE_DIV
+    return x / y;
+#else
+    return __fdividef(x, y);
+#endif
+}
 #ifndef RL_RTC_NOINLINE  // experiment switch (tools/build_alt.py): 1 = prim_roots out of line, 2 = + closest / shadow / n1-n2
 #define RL_RTC_NOINLINE 0
 #endif
@@ -59,11 +72,11 @@ RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], un
         case PK_RTC_SPHERE: {  // sphere.rs:35-59 (numerically robust quarter-discriminant form)
             float a = dot(d, d);
             float hb = dot(d, o);
-            float tc = -hb / a;
+            float tc = fdiv(-hb, a);
             float3 perp = fma3(d, tc, o);
             float disc = a * (1.0f - dot(perp, perp));
             if (disc >= 0.0f) {
-                float q = sqrtf(disc) / a;
+                float q = fdiv(sqrtf(disc), a);
                 ts[0] = tc - q;
                 ts[1] = tc + q;
                 n = 2;
@@ -72,15 +85,15 @@ RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], un
         }
         case PK_RTC_PLANE: {  // plane.rs:26-39
             if (!(fabsf(d.y) < RTC_EPS)) {
-                ts[0] = -o.y / d.y;
+                ts[0] = fdiv(-o.y, d.y);
                 n = 1;
             }
             break;
         }
         case PK_RTC_CUBE: {  // cube.rs:38-79
-            float ax = (-1.0f - o.x) / d.x, bx = (1.0f - o.x) / d.x;
-            float ay = (-1.0f - o.y) / d.y, by = (1.0f - o.y) / d.y;
-            float az = (-1.0f - o.z) / d.z, bz = (1.0f - o.z) / d.z;
+            float ax = fdiv(-1.0f - o.x, d.x), bx = fdiv(1.0f - o.x, d.x);
+            float ay = fdiv(-1.0f - o.y, d.y), by = fdiv(1.0f - o.y, d.y);
+            float az = fdiv(-1.0f - o.z, d.z), bz = fdiv(1.0f - o.z, d.z);
             float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
             float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             if (!(tmin > tmax)) {
@@ -94,11 +107,11 @@ RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], un
             float a = d.x * d.x + d.z * d.z;
             if (!(fabsf(a) < RTC_EPS)) {
                 float hb = o.x * d.x + o.z * d.z;
-                float tc = -hb / a;
+                float tc = fdiv(-hb, a);
                 float px = fmaf(d.x, tc, o.x), pz = fmaf(d.z, tc, o.z);
                 float disc = a * (1.0f - (px * px + pz * pz));
                 if (disc >= 0.0f) {
-                    float q = sqrtf(disc) / a;
+                    float q = fdiv(sqrtf(disc), a);
                     float t0 = tc - q, t1 = tc + q;
                     float y0 = fmaf(t0, d.y, o.y);
                     if (y0 > p.ymin && y0 < p.ymax) ts[n++] = t0;
@@ -108,12 +121,12 @@ RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], un
             }
             if ((p.flags & 1) && !(fabsf(d.y) < RTC_EPS)) {
                 if (p.ymin > -RL_INF) {
-                    float t = (p.ymin - o.y) / d.y;
+                    float t = fdiv(p.ymin - o.y, d.y);
                     float x = fmaf(t, d.x, o.x), z = fmaf(t, d.z, o.z);
                     if (x * x + z * z <= 1.0f) { *tags |= 1u << (2 * n); ts[n++] = t; }
                 }
                 if (p.ymax < RL_INF) {
-                    float t = (p.ymax - o.y) / d.y;
+                    float t = fdiv(p.ymax - o.y, d.y);
                     float x = fmaf(t, d.x, o.x), z = fmaf(t, d.z, o.z);
                     if (x * x + z * z <= 1.0f) { *tags |= 2u << (2 * n); ts[n++] = t; }
                 }
@@ -127,12 +140,12 @@ RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], un
             bool a0 = fabsf(a) < RTC_EPS, b0 = fabsf(b) < RTC_EPS;
             if (a0 && b0) {
             } else if (a0) {
-                ts[n++] = -c / (2.0f * b);
+                ts[n++] = fdiv(-c, 2.0f * b);
             } else {
                 float disc = b * b - 4.0f * a * c;
                 if (disc >= 0.0f) {
                     float s = sqrtf(disc);
-                    float t0 = (-b - s) / (2.0f * a), t1 = (-b + s) / (2.0f * a);
+                    float t0 = fdiv(-b - s, 2.0f * a), t1 = fdiv(-b + s, 2.0f * a);
                     float y0 = fmaf(t0, d.y, o.y);
                     if (y0 > p.ymin && y0 < p.ymax) ts[n++] = t0;
                     float y1 = fmaf(t1, d.y, o.y);
@@ -141,12 +154,12 @@ RL_ROOTS_FN int prim_roots(const RtcPrim& p, float3 o, float3 d, float ts[4], un
             }
             if ((p.flags & 1) && !(fabsf(d.y) < RTC_EPS)) {
                 if (p.ymin > -RL_INF) {
-                    float t = (p.ymin - o.y) / d.y;
+                    float t = fdiv(p.ymin - o.y, d.y);
                     float x = fmaf(t, d.x, o.x), z = fmaf(t, d.z, o.z);
                     if (x * x + z * z <= fabsf(p.ymin)) { *tags |= 1u << (2 * n); ts[n++] = t; }
                 }
                 if (p.ymax < RL_INF) {
-                    float t = (p.ymax - o.y) / d.y;
+                    float t = fdiv(p.ymax - o.y, d.y);
                     float x = fmaf(t, d.x, o.x), z = fmaf(t, d.z, o.z);
                     if (x * x + z * z <= fabsf(p.ymax)) { *tags |= 2u << (2 * n); ts[n++] = t; }
                 }
