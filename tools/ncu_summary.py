@@ -33,7 +33,7 @@ def get(name, default=None):
 
 rd, wr = get("dram__bytes_read.sum", 0.0), get("dram__bytes_write.sum", 0.0)
 d = {
-    "workload": wl, "kernel": vals[kn], "source": f"ncu --set full --clock-control none, {rep.split('/')[-1]}",
+    "workload": wl, "kernel": vals[kn], "source": f"ncu {'--set full' if 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio' in hdr else '(short metric list)'} --clock-control none, {rep.split('/')[-1]}",
     "gpu_time_ms_under_ncu": get("gpu__time_duration.sum"),
     "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
     "issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
