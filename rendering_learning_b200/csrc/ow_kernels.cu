@@ -186,7 +186,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
         } else if (fabsf(c.w) >= OW_BIG_RADIUS) {
             // a huge sphere seen from near its surface (the r = 1000 ground of the cover scene): r^2 - |perp|^2
             // cancels ~7 digits, more than f32 has.  One such primitive sits near the BVH root, so its
-            // quadratic is evaluated in f64 (B200 runs FP64 at half the FP32 rate; the cost is one test per ray).
+            // quadratic's cancelling terms are evaluated in f64 (the cost is one test per ray).
             // o - centre in f64 as well: in f32 the ray's height above an r = 1000 sphere keeps 6e-5 of absolute precision,
             // which a grazing ray turns into 4e-4 of relative error in t (measured on the reference's scattered rays)
             double ox = (double)o.x - fma((double)dc.x, (double)time, (double)c.x);
@@ -198,10 +198,15 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
             double cc = ox * ox + oy * oy + oz * oz - (double)c.w * (double)c.w;
             double disc = hbd * hbd - a * cc;
             if (disc < 0.0) return;
-            double sq = sqrt(disc);
-            t = (float)((-hbd - sq) / a);
+            // The cancellations (|oc|^2 - r^2, hbd^2 - a cc) are done, in f64; the roots follow in f32 through the form that
+            // has none left: q = -(hb + sign(hb) sqrt(disc)), roots q / a and cc / q.  (The f64 square root and the two f64
+            // divisions this replaces were 2.3 % of the cover scene's warp instructions.)
+            const float sq = fast_sqrt((float)disc), hbf = (float)hbd;
+            const float q = hbf < 0.0f ? sq - hbf : -(sq + hbf);
+            const float ra = __fdividef(q, (float)a), rb = __fdividef((float)cc, q);
+            t = fminf(ra, rb);
             if (!(t >= tmin && t <= h.t)) {
-                t = (float)((-hbd + sq) / a);
+                t = fmaxf(ra, rb);
                 if (!(t >= tmin && t <= h.t)) return;
             }
         } else {
