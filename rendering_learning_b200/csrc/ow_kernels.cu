@@ -230,7 +230,7 @@ __device__ __forceinline__ void ow_leaf_test(const DevScene& sc, int ref, const 
     } else if ((PRIMS & PRIMS_TRIS) && type == REF_TRI) {  // flat/plane.rs:51-80 + flat/triangle.rs:60-67, the reference's own form
         // Round 1 ran the watertight ray-space test here (device.cuh tri_hit, still the RTC path): ~90 instructions with its
         // per-ray axis permutation selects, 20 % of the Cornell-box + spot warp instructions at 5 - 6 lanes
-        // (profiles/r02_lines_ow_c5_4k_256.txt).  The plane form is the quad test with a different acceptance: ~35.
+        // (profiles/r02_lines_ow_c5_4k_256_watertight_triangles.txt).  The plane form is the quad test with a different acceptance: ~35.
         if (ref == self_ref) return;
         const OwTriPlane& tp = sc.tri_plane[idx];
         float4 n4 = tp.n;
