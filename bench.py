@@ -13,7 +13,8 @@ NVLink and store finished items straight into rank 0's partial-sum buffer; rank 
              atomics in a separate instrumented pass with the same seed.
   e2e        the same metric through the public API — the literal `Camera.render(world)` call (scenes.py worlds, the
              reference's own types): lower the object tree, rl_scene_upload (flatten, H2D, LBVH build), render, D2H of
-             the framebuffer into PAGEABLE host memory, f64 Canvas — every step.  `e2e.prepared` is the same call given
+             the framebuffer into PAGEABLE host memory, Canvas (which holds the f32 frame and widens it to the
+             reference's f64 Colors on first pixel access) — every step.  `e2e.prepared` is the same call given
              an already-lowered scene (`Camera.render(scene_desc)`, the caller keeps the lowering).
   roofline   what bounds the kernel is instruction issue x SIMT lane utilisation (bound = "issue"), not HBM and not
              tensor cores (no stage is a dense contraction, the working set is L1 / L2 resident): `achieved` / `peak` /
