@@ -412,6 +412,7 @@ static int upload_flat(rl_ctx* c, const FlatScene& fs, int n_scene_nodes) {
         mi.flavor = fs.flavor;
         mi.material = u.material;
         mi.node = u.node;
+        mi.report_node = (fs.flavor == RL_FLAVOR_RTC && u.node >= 0 && u.node < (int)fs.ord_node.size()) ? fs.ord_node[u.node] : u.node;
         mi.tri_first = u.tri_first;
         mi.bvh_first = u.bvh_first;
         mi.xf = u.xf;

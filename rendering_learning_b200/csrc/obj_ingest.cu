@@ -561,7 +561,7 @@ __global__ void k_mesh_instance(ObjMesh m, int n, MeshInstance inst, TriVerts* _
         aabb[6 * (size_t)bi + 3 + k] = __fadd_rn(hi, __fmul_rn(__fmul_rn(4.0f, 1.1920929e-7f), fmaxf(fabsf(hi), 1e-3f)));
     }
     refs[bi] = make_ref(REF_TRI, idx);
-    node_ids[bi] = inst.node;
+    node_ids[bi] = inst.report_node;
 }
 
 // object-space bounds of the parsed points (the flattener needs the mesh's extent without seeing its triangles)

@@ -21,7 +21,8 @@ struct ObjMesh {
 struct MeshInstance {
     double fwd[3][4];  // object -> world
     double inv[3][4];  // world -> object (normals: inv^T)
-    int flavor, material, node;
+    int flavor, material, node;  // node: what the triangles carry (RTC: the DFS leaf ordinal, OW: the caller's node id)
+    int report_node;             // the caller's node id (rl_scene_download's prim_node)
     int tri_first;     // first slot in tri_verts / tri_shade
     int bvh_first;     // first slot in the LBVH input arrays
     int xf;            // RTC: index + 1 of the world -> pattern transform of the material's pattern (0 = none)
