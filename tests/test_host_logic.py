@@ -186,3 +186,29 @@ def test_ow_checkpoint_bincode_layout():
     assert merged.samples == 14 and np.array_equal(merged.data, 2 * data)
     with pytest.raises(ValueError):
         ow.Canvas.from_bincode(blob[:-1])
+
+
+def test_canvases_hold_the_device_f32_frame_and_widen_on_access():
+    """`Camera.render` hands the Canvas the f32 frame the device wrote; the reference's `Color` is f64, so every accessor
+    sees f64 — widened once, on first access — and the 8-bit / PPM / bincode results are those of the widened frame."""
+    from rendering_learning_b200 import ow, rtc
+    rng = np.random.default_rng(3)
+    f32 = rng.uniform(-0.2, 1.4, size=(6, 8, 3)).astype(np.float32)
+    f32[0, 0] = (np.nan, 0.5, 2.0)
+    c = rtc.Canvas(8, 6, f32)
+    assert c._data.dtype == np.float32 and c._data is not None          # no copy made at construction
+    wide = rtc.Canvas(8, 6, f32.astype(np.float64))
+    assert np.array_equal(c.to_u8(), wide.to_u8()) and c.ppm() == wide.ppm()
+    assert c.data.dtype == np.float64 and c._data.dtype == np.float64   # widened once, kept
+    assert c.at(1, 2) == tuple(f32[2, 1].astype(np.float64))
+    c.write((1, 2), (0.25, 0.5, 0.75))
+    assert c.at(1, 2) == (0.25, 0.5, 0.75) and rtc.Canvas(2, 2).data.dtype == np.float64
+
+    sums = np.abs(f32[1:]).astype(np.float32) * 10.0
+    a = ow.Canvas(10, 8, 5, sums)
+    b = ow.Canvas(10, 8, 5, sums.astype(np.float64))
+    assert a._data.dtype == np.float32
+    assert a == b and np.array_equal(a.to_u8(), b.to_u8()) and a.to_bincode() == b.to_bincode()
+    m = a.merge(b)
+    assert m.samples == 20 and m.data.dtype == np.float64 and np.array_equal(m.data, 2.0 * sums.astype(np.float64))
+    assert ow.Canvas.from_bincode(a.to_bincode()) == b
