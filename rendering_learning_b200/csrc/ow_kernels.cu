@@ -1717,10 +1717,13 @@ K6 pick_k6(int prims, int minb, bool instrumented) {
 #undef RL_K6
 }
 
+#ifndef RL_K5_HI  // resident CTAs per SM the production kernel is compiled for (experiment builds: 5 = 48 registers)
+#define RL_K5_HI 4
+#endif
 template <bool TRACE>
 K5 pick_k5(int prims, int minb, bool instrumented) {
 #define RL_K5(P_)                                                                                                     \
-    (minb >= 4 ? (instrumented ? (K5)k_ow_render5<true, 4, P_, TRACE> : (K5)k_ow_render5<false, 4, P_, TRACE>)       \
+    (minb >= 4 ? (instrumented ? (K5)k_ow_render5<true, RL_K5_HI, P_, TRACE> : (K5)k_ow_render5<false, RL_K5_HI, P_, TRACE>) \
                : (instrumented ? (K5)k_ow_render5<true, 3, P_, TRACE> : (K5)k_ow_render5<false, 3, P_, TRACE>))
     switch (prims) {
         case PRIMS_SPHERES: return RL_K5(PRIMS_SPHERES);
