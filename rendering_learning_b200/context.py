@@ -26,6 +26,17 @@ class Context:
         self.h = h
         self.device_id = device_id
         self._scene = None
+        # True: frames returned by render_* live in page-locked host memory (torch's caching host allocator recycles the
+        # block when the array is dropped), so the device -> host copy is one DMA instead of a staged copy into fresh
+        # pageable pages — at 4K that copy, not the kernel, is the RTC frame time.  Default False: what a plain caller has.
+        self.pinned_frames = False
+
+    def _frame(self, shape, dtype):
+        if self.pinned_frames:
+            import torch
+            t = torch.empty(shape, dtype=torch.float32 if dtype == np.float32 else torch.uint8, pin_memory=True)
+            return t.numpy()  # shares the tensor's storage and keeps it alive
+        return np.empty(shape, dtype)
 
     def close(self):
         if getattr(self, "h", None):
@@ -162,7 +173,7 @@ class Context:
     # ---- renders (host buffers) ----------------------------------------------------------------
     def render_rtc(self, cam: A.rl_rtc_camera, aa_samples: int = 1, out: np.ndarray | None = None):
         if out is None:
-            out = np.empty((cam.vsize, cam.hsize, 3), np.float32)
+            out = self._frame((cam.vsize, cam.hsize, 3), np.float32)
         stats = A.rl_stats()
         self._check(self.lib.rl_render_rtc(self.h, C.byref(cam), C.c_uint32(aa_samples),
                                            out.ctypes.data_as(C.POINTER(C.c_float)),
@@ -171,7 +182,7 @@ class Context:
 
     def render_rtc_u8(self, cam: A.rl_rtc_camera, aa_samples: int = 1):
         """render + Canvas::ppm's 8-bit `translate` on the device: [H][W][3] uint8"""
-        out = np.empty((cam.vsize, cam.hsize, 3), np.uint8)
+        out = self._frame((cam.vsize, cam.hsize, 3), np.uint8)
         stats = A.rl_stats()
         self._check(self.lib.rl_render_rtc_u8(self.h, C.byref(cam), C.c_uint32(aa_samples),
                                               out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(stats)))
@@ -179,7 +190,7 @@ class Context:
 
     def render_ow_u8(self, cam: A.rl_ow_camera, first_sample: int = 0):
         """render + pixel_data / linear_to_srgb / to_u8 on the device: [H][W][3] uint8"""
-        out = np.empty((self.ow_image_height(cam), cam.image_width, 3), np.uint8)
+        out = self._frame((self.ow_image_height(cam), cam.image_width, 3), np.uint8)
         stats = A.rl_stats()
         self._check(self.lib.rl_render_ow_u8(self.h, C.byref(cam), C.c_uint32(first_sample),
                                              out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(stats)))
@@ -194,7 +205,7 @@ class Context:
     def render_ow(self, cam: A.rl_ow_camera, first_sample: int = 0, out: np.ndarray | None = None):
         h = self.ow_image_height(cam)
         if out is None:
-            out = np.empty((h, cam.image_width, 3), np.float32)
+            out = self._frame((h, cam.image_width, 3), np.float32)
         stats = A.rl_stats()
         self._check(self.lib.rl_render_ow(self.h, C.byref(cam), C.c_uint32(first_sample),
                                           out.ctypes.data_as(C.POINTER(C.c_float)),
