@@ -414,3 +414,25 @@ def test_ties_follow_the_tree_order_not_the_node_ids(ctx, oracle):
         inv = np.full(n + 1, -1)
         inv[np.asarray(perm)] = np.arange(n)
         assert np.array_equal(inv[hits["node"]], hits0["node"]) and np.array_equal(hits["t"], hits0["t"])
+
+
+def test_pinned_frames_are_the_same_frames(ctx):
+    """Context.pinned_frames only changes where the returned frame lives (page-locked memory recycled by the caching host
+    allocator): same bits, for the float and the 8-bit entry points, and a frame stays valid after later renders."""
+    sc = scenes.rtc_mirror_scene(320, 200)
+    ctx.scene_upload(sc.world.lower())
+    cam = sc.camera.abi()
+    a, _ = ctx.render_rtc(cam, 1)
+    a8, _ = ctx.render_rtc_u8(cam, 1)
+    ctx.pinned_frames = True
+    try:
+        b, _ = ctx.render_rtc(cam, 1)
+        keep = b.copy()
+        b8, _ = ctx.render_rtc_u8(cam, 1)
+        for _ in range(3):  # later frames must come from other blocks while `b` is alive
+            c, _ = ctx.render_rtc(cam, 2)
+        assert np.array_equal(a, b) and np.array_equal(a8, b8) and np.array_equal(b, keep) and not np.array_equal(c, b)
+        cv = sc.camera.render(sc.world, ctx=ctx)
+        assert np.array_equal(cv.to_u8(), u8(a.astype(np.float64)))
+    finally:
+        ctx.pinned_frames = False
