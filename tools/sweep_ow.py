@@ -62,6 +62,11 @@ else:
           for v in itertools.product((3, 4), (256, 320, 384, 512), (6, 8, 12), (8, 16, 24), (6, 8, 12))]
 
 t0 = time.time()
+if mode == "c4":  # thresholds of the spheres-only instantiation only
+    grid = [{}] + [{"ow.svc_min": a, "ow.leaf_min": b} for a in (20, 22, 24, 26, 28) for b in (6, 8, 10, 12)]
+    run("C4_1200x675_500spp", scenes.ow_cover_world(), scenes.ow_cover_params(), grid, reps=3)
+    print(json.dumps({"seconds": time.time() - t0}), flush=True)
+    sys.exit(0)
 if mode == "c5":  # thresholds of the triangle-scene instantiation only
     grid = [{}] + [{"ow.svc_min": a, "ow.leaf_min": b} for a in (12, 16, 20, 24, 28) for b in (4, 8, 12, 16)] + [{"ow.minb": 3}]
     run("C5_1920x1080_64spp", scenes.ow_cow_world(), scenes.ow_cow_params(image_width=1920, samples_per_pixel=64), grid, reps=3)
