@@ -346,11 +346,9 @@ struct Path {
     int self_ref;
 };
 
+// t_min of a ray: the reference's f64 1e-10 (camera.rs:242) cannot hold for f32 origins; 1e-5 x max|origin_k| + 1e-6 in units of
+// the NORMALISED direction (the kernels normalise every direction when its traversal starts).
 // hit record + material evaluation for one bounce; returns false when the path ends
-__device__ __forceinline__ float ow_tmin(const Path& p) {
-    return fmaf(1e-5f, max_abs(p.o), 1e-6f) * rsqrtf(dot(p.d, p.d));
-}
-
 template <bool COUNT, int PRIMS = PRIMS_ALL>
 __device__ __forceinline__ bool ow_shade(const DevScene& sc, const OwCam& cam, Path& p, const OwHit& h, uint4 rnd,
                                          float3& rad, LocalCount<COUNT>& lc);
@@ -789,7 +787,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render5(DevScene sc, OwCam cam
             p.d = p.d * rsqrtf(dot(p.d, p.d));
             inv_d = safe_inv_fast(p.d);
             oi = p.o * inv_d;
-            tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // ow_tmin with |d| = 1
+            tmin = fmaf(1e-5f, max_abs(p.o), 1e-6f);  // t_min, see Path
             if ((PRIMS & PRIMS_MEDIA) && !TRACE)
                 ray_rnd = philox(make_uint4(pixel, (unsigned)(cam.first_sample + s), (unsigned)(cam.max_depth - p.depth + 1), 2u), key).x;
             hit.t = RL_INF; hit.ref = -1; hit.b1 = hit.b2 = 0.0f;
@@ -1033,7 +1031,7 @@ __global__ void __launch_bounds__(256, MINB) k_ow_render6(DevScene sc, OwCam cam
                 if (PRIMS & PRIMS_MEDIA) ray_rnd = (unsigned)SLI(RND, got);
                 inv_d = safe_inv_fast(d);
                 oi = o * inv_d;
-                tmin = fmaf(1e-5f, max_abs(o), 1e-6f);  // ow_tmin with |d| = 1
+                tmin = fmaf(1e-5f, max_abs(o), 1e-6f);  // t_min, see Path
                 if (PRIMS & PRIMS_TRIS) shear = make_shear(o, d);
                 stack_reset(st);
                 node = sc.n_bvh_prims > 0 ? 0 : TRAV_END;
